@@ -1,0 +1,77 @@
+/* kronmult_b200.h -- C ABI of the B200-native kronmult library (libkronmult_b200.so).
+ *
+ * The reference (project-asgard/kronmult993) has no C ABI: its GPU flavour exports two C++ template
+ * specialisations (kronmult_gpu/kronmult.cu:202-211 double, :216-224 float; declared at
+ * kronmult_gpu/kronmult.cuh:28-32) and pow_int (kronmult.cu:11-15, kronmult.cuh:10).  The functions
+ * below are what an FFI for that path binds; the C++ specialisations in include/kronmult.cuh are thin
+ * wrappers over them.  Plain pointers and sizes only; every function returns a cudaError_t value as
+ * int (0 = cudaSuccess) and never throws.
+ *
+ * Common arguments (identical meaning to kronmult.cuh:12-26):
+ *   d    matrix_count          number of Kronecker factors
+ *   n    matrix_size           each factor is n x n, column-major
+ *   A    matrix_list_batched   DEVICE array of nb*d DEVICE pointers, item k uses A[k*d .. k*d+d)
+ *   lda  matrix_stride         leading dimension of every factor (>= n)
+ *   in   input_batched         DEVICE array of nb DEVICE pointers to n^d-element vectors (may be clobbered)
+ *   out  output_batched        DEVICE array of nb DEVICE pointers; out[k] += kron(A_k) * in[k]; may repeat
+ *   ws   workspace_batched     DEVICE array of nb DEVICE pointers (may be clobbered; may be NULL here:
+ *                              this implementation never dereferences it)
+ *   nb   nb_batch              number of batch items (0 is a no-op)
+ */
+#ifndef KRONMULT_B200_H
+#define KRONMULT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* replaces pow_int, kronmult_gpu/kronmult.cuh:10 (kronmult.cu:11-15) */
+int kronmult_pow_int(int number, int power);
+
+/* replace kronmult_batched<double> / <float>, kronmult_gpu/kronmult.cuh:28-32
+ * (kronmult.cu:202-211 / :216-224): blocking, legacy default stream, returns after
+ * cudaDeviceSynchronize() like kronmult.cu:196. */
+int kronmult_batched_f64(int d, int n, const double *const *A, int lda, double **in, double **out,
+                         double **ws, int nb);
+int kronmult_batched_f32(int d, int n, const float *const *A, int lda, float **in, float **out,
+                         float **ws, int nb);
+
+/* stream-ordered variants of the same call (no reference counterpart: the reference is blocking,
+ * kronmult.cu:191-196).  `stream` is a cudaStream_t; no host synchronisation is performed. */
+int kronmult_batched_f64_async(int d, int n, const double *const *A, int lda, double **in, double **out,
+                               double **ws, int nb, void *stream);
+int kronmult_batched_f32_async(int d, int n, const float *const *A, int lda, float **in, float **out,
+                               float **ws, int nb, void *stream);
+
+/* Host-buffer entry points with the signature of the reference's CPU flavour
+ * (kronmult_omp/kronmult.hpp:77-80): every pointer array and every pointee lives in HOST memory.
+ * The library stages chunks of items through pinned buffers, runs the device path on `device`
+ * (-1 = current device) and writes the accumulated outputs back; input/workspace are not modified. */
+int kronmult_batched_host_f64(int d, int n, const double *const *A, int lda, double **in, double **out,
+                              double **ws, int nb, int device);
+int kronmult_batched_host_f32(int d, int n, const float *const *A, int lda, float **in, float **out,
+                              float **ws, int nb, int device);
+
+/* Multi-GPU partitioner (no reference counterpart; BASELINE.json north_star): assign every item to one
+ * of n_ranks owners such that all items sharing an output pointer get the same owner and the item
+ * counts are balanced (longest-processing-time greedy over output groups).  `out` is a HOST array of
+ * nb output pointers (any integer key works); owner[k] in [0, n_ranks) is written for every item.
+ * Groups larger than `split_threshold` items (0 = never) are instead split evenly over all ranks and
+ * flagged in needs_reduce[k] = 1: their partial outputs must be summed across ranks afterwards. */
+int kronmult_partition_by_output(const void *const *out, int nb, int n_ranks, long long split_threshold,
+                                 int *owner, unsigned char *needs_reduce);
+
+/* Introspection used by the test-suite and bench.py. */
+const char *kronmult_b200_version(void);
+/* number of kernels this library has launched in this process so far */
+long long kronmult_b200_launch_count(void);
+/* name of the kernel family chosen by the most recent call on this thread ("tiny", "generic", ...) */
+const char *kronmult_b200_last_path(void);
+/* 0 = automatic dispatch; otherwise force a kernel family (see kronmult993_b200/csrc/dispatch.h).
+ * Unsupported combinations make the next call return cudaErrorInvalidValue.  For tests. */
+int kronmult_b200_force_path(int path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KRONMULT_B200_H */

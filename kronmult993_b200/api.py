@@ -1,0 +1,186 @@
+"""Python mirror of the reference's ``kronmult_batched`` operator, bound to the C ABI.
+
+The reference (project-asgard/kronmult993) is a C++ library; its operator is
+``kronmult_batched<T>(matrix_count, matrix_size, matrix_list_batched, matrix_stride, input_batched,
+output_batched, workspace_batched, nb_batch)`` (``kronmult_gpu/kronmult.cuh:28-32``).  This module
+exposes the same operator with the same argument names, order and meaning on top of
+``include/kronmult_b200.h`` via ctypes so that the parity tests read like the reference's own
+(``tests/kronmult_test_gpu.cpp:43-46``).  Pointer arrays are ``torch.int64`` tensors (or raw integer
+addresses) that live on the device, exactly as the reference requires (``kronmult.cuh:22``).
+
+There is no fallback of any kind: if ``libkronmult_b200.so`` cannot be loaded the import of the
+operator raises, and a CUDA error code from the library is raised as ``KronmultError`` (the reference's
+harness does the same with ``checkCudaErrorCode``, ``tests/utils/utils_gpu.h:11-17``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Union
+
+import torch
+
+from . import build as _build
+
+PATH_AUTO, PATH_GENERIC, PATH_TINY, PATH_REGTILE, PATH_DMMA = 0, 1, 2, 3, 4
+PATHS = {"auto": PATH_AUTO, "generic": PATH_GENERIC, "tiny": PATH_TINY, "regtile": PATH_REGTILE, "dmma": PATH_DMMA}
+
+# every symbol include/kronmult_b200.h declares (tests/test_abi.py checks the header against this)
+C_SYMBOLS = (
+    "kronmult_pow_int",
+    "kronmult_batched_f64",
+    "kronmult_batched_f32",
+    "kronmult_batched_f64_async",
+    "kronmult_batched_f32_async",
+    "kronmult_batched_host_f64",
+    "kronmult_batched_host_f32",
+    "kronmult_partition_by_output",
+    "kronmult_b200_version",
+    "kronmult_b200_launch_count",
+    "kronmult_b200_last_path",
+    "kronmult_b200_force_path",
+)
+# the C++ drop-in symbols of include/kronmult.cuh (same mangling as the reference library)
+CXX_SYMBOLS = (
+    "_Z7pow_intii",
+    "_Z16kronmult_batchedIdE9cudaErroriiPKPKT_iPPS1_S7_S7_i",
+    "_Z16kronmult_batchedIfE9cudaErroriiPKPKT_iPPS1_S7_S7_i",
+)
+
+
+class KronmultError(RuntimeError):
+    def __init__(self, code: int, where: str):
+        self.code = int(code)
+        super().__init__(f"{where}: CUDA error {self.code}")
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load_library() -> ctypes.CDLL:
+    """Load (building first if the sources are newer) the CUDA library.  Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if os.environ.get("KRONMULT_B200_NO_BUILD") != "1":
+        try:
+            path = _build.build_library()
+        except Exception:
+            if not os.path.exists(path):
+                raise
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing and could not be built: kronmult993_b200 has no non-CUDA path")
+    lib = ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+    c_int, c_vp = ctypes.c_int, ctypes.c_void_p
+    for sfx in ("f64", "f32"):
+        f = getattr(lib, f"kronmult_batched_{sfx}")
+        f.restype, f.argtypes = c_int, [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int]
+        f = getattr(lib, f"kronmult_batched_{sfx}_async")
+        f.restype, f.argtypes = c_int, [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp]
+        f = getattr(lib, f"kronmult_batched_host_{sfx}")
+        f.restype, f.argtypes = c_int, [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int]
+    lib.kronmult_pow_int.restype, lib.kronmult_pow_int.argtypes = c_int, [c_int, c_int]
+    lib.kronmult_partition_by_output.restype = c_int
+    lib.kronmult_partition_by_output.argtypes = [c_vp, c_int, c_int, ctypes.c_longlong, c_vp, c_vp]
+    lib.kronmult_b200_version.restype = ctypes.c_char_p
+    lib.kronmult_b200_launch_count.restype = ctypes.c_longlong
+    lib.kronmult_b200_last_path.restype = ctypes.c_char_p
+    lib.kronmult_b200_force_path.restype, lib.kronmult_b200_force_path.argtypes = c_int, [c_int]
+    _lib = lib
+    return lib
+
+
+def _addr(x) -> int:
+    if x is None:
+        return 0
+    if isinstance(x, torch.Tensor):
+        if x.dtype != torch.int64:
+            raise TypeError("pointer arrays must be int64 tensors of device addresses")
+        if not x.is_contiguous():
+            raise ValueError("pointer arrays must be contiguous")
+        return x.data_ptr()
+    return int(x)
+
+
+def _suffix(dtype) -> str:
+    if dtype in (torch.float64, "f64", "double"):
+        return "f64"
+    if dtype in (torch.float32, "f32", "float"):
+        return "f32"
+    # the reference only instantiates float and double (kronmult.cu:202-224): other T = link error
+    raise TypeError(f"kronmult_batched is defined for float32 and float64 only, got {dtype}")
+
+
+def pow_int(number: int, power: int) -> int:
+    """``pow_int`` of the reference (``kronmult_gpu/kronmult.cuh:10``)."""
+    return load_library().kronmult_pow_int(int(number), int(power))
+
+
+def kronmult_batched(matrix_count: int, matrix_size: int, matrix_list_batched, matrix_stride: int, input_batched,
+                     output_batched, workspace_batched, nb_batch: int, *, dtype=torch.float64,
+                     stream: Union[None, int, "torch.cuda.Stream"] = None) -> None:
+    """``output[k] += kron(matrix_list[k]) @ input[k]`` for ``k < nb_batch`` on the current device.
+
+    Same argument list as the reference operator.  With ``stream=None`` the call is blocking and
+    runs on the legacy default stream, like ``kronmult.cu:191-196``; passing a ``torch.cuda.Stream``
+    (or a raw ``cudaStream_t``) uses the stream-ordered entry point and does not synchronise.
+    """
+    lib = load_library()
+    sfx = _suffix(dtype)
+    args = [int(matrix_count), int(matrix_size), _addr(matrix_list_batched), int(matrix_stride),
+            _addr(input_batched), _addr(output_batched), _addr(workspace_batched), int(nb_batch)]
+    if stream is None:
+        code = getattr(lib, f"kronmult_batched_{sfx}")(*args)
+    else:
+        handle = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+        code = getattr(lib, f"kronmult_batched_{sfx}_async")(*args, handle)
+    if code != 0:
+        raise KronmultError(code, "kronmult_batched")
+
+
+def kronmult_batched_host(matrix_count: int, matrix_size: int, matrix_list_batched, matrix_stride: int,
+                          input_batched, output_batched, workspace_batched, nb_batch: int, *,
+                          dtype=torch.float64, device: int = -1) -> None:
+    """Host-memory flavour (signature of ``kronmult_omp/kronmult.hpp:77-80``): pointer arrays are raw
+    addresses of HOST arrays of HOST pointers; the library stages the data through the GPU."""
+    lib = load_library()
+    sfx = _suffix(dtype)
+    code = getattr(lib, f"kronmult_batched_host_{sfx}")(
+        int(matrix_count), int(matrix_size), _addr(matrix_list_batched), int(matrix_stride), _addr(input_batched),
+        _addr(output_batched), _addr(workspace_batched), int(nb_batch), int(device))
+    if code != 0:
+        raise KronmultError(code, "kronmult_batched_host")
+
+
+def run_problem(problem, *, stream=None, path: str = "auto") -> None:
+    """Apply the operator to a ``batch.KronProblem`` in place (``problem.out_slab`` accumulates)."""
+    A, i, o, w = problem.pointer_arrays()
+    force_path(path)
+    try:
+        kronmult_batched(problem.d, problem.n, A, problem.lda, i, o, w, problem.nb, dtype=problem.dtype,
+                         stream=stream)
+    finally:
+        force_path("auto")
+
+
+def force_path(path: Union[str, int]) -> None:
+    code = load_library().kronmult_b200_force_path(PATHS[path] if isinstance(path, str) else int(path))
+    if code != 0:
+        raise KronmultError(code, "kronmult_b200_force_path")
+
+
+def last_path() -> str:
+    return load_library().kronmult_b200_last_path().decode()
+
+
+def launch_count() -> int:
+    return int(load_library().kronmult_b200_launch_count())
+
+
+def version() -> str:
+    return load_library().kronmult_b200_version().decode()

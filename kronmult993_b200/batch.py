@@ -280,3 +280,28 @@ def reference_case(name: str, dtype=torch.float64, device="cpu", seed: int = 993
         nb = min(nb, nb_cap)
     return make_problem(dimension, degree, nb, dtype, device, seed, alias="ref", nb_distinct=nb_distinct,
                         matrices="reftest")
+
+
+def from_host(hp: HostProblem, device="cuda") -> KronProblem:
+    """Upload a numpy problem (e.g. a golden fixture) to a torch device."""
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    dtype = torch.float64 if hp.in_slab.dtype == np.float64 else torch.float32
+    N = hp.N
+    n_out = int(hp.out_slab.size // N)
+    return KronProblem(hp.d, hp.n, hp.lda, hp.nb, dtype, t(hp.mat_slab), t(hp.mat_off.astype(np.int64)),
+                       t(hp.in_slab), t(hp.in_off.astype(np.int64)), t(hp.out_slab), t(hp.out_off.astype(np.int64)),
+                       n_out, int(np.unique(hp.mat_off).size))
+
+
+def save_host(path: str, hp: HostProblem, **extra) -> None:
+    np.savez_compressed(path, d=hp.d, n=hp.n, lda=hp.lda, nb=hp.nb, mat_slab=hp.mat_slab, mat_off=hp.mat_off,
+                        in_slab=hp.in_slab, in_off=hp.in_off, out_slab=hp.out_slab, out_off=hp.out_off, **extra)
+
+
+def load_host(path: str) -> "tuple[HostProblem, dict]":
+    z = np.load(path)
+    hp = HostProblem(int(z["d"]), int(z["n"]), int(z["lda"]), int(z["nb"]), z["mat_slab"], z["mat_off"],
+                     z["in_slab"], z["in_off"], z["out_slab"], z["out_off"])
+    extra = {k: z[k] for k in z.files if k not in ("d", "n", "lda", "nb", "mat_slab", "mat_off", "in_slab",
+                                                    "in_off", "out_slab", "out_off")}
+    return hp, extra

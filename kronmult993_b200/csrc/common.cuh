@@ -1,0 +1,38 @@
+// common.cuh -- small device/host helpers shared by every kernel family.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace kron
+{
+
+// Kernel families (values are the public `kronmult_b200_force_path` codes).
+enum Path : int
+{
+    PATH_AUTO    = 0,
+    PATH_GENERIC = 1, // shared-memory tiles, runtime d, any n <= 32, multi-pass for large n^d
+    PATH_TINY    = 2, // one thread per item, everything in registers (n^d <= 16)
+    PATH_REGTILE = 3, // register-tiled in-place mode products, compile-time (n,d), n in {3,4,5,6}
+    PATH_DMMA    = 4, // n = 8 on the FP64 tensor pipe (mma.sync m8n8k4), double only
+};
+
+__host__ __device__ constexpr int ipow(int b, int e)
+{
+    int v = 1;
+    for (int i = 0; i < e; ++i) v *= b;
+    return v;
+}
+
+// Thread-safe `*addr += v` without a return value: lowers to RED.E.ADD.{F32,F64} on sm_100a.
+// Every final accumulation in this library goes through an atomic-class add so that ANY aliasing of
+// output pointers (equal pointers, partial overlap, non-adjacent repeats) stays correct, like the
+// reference's element-wise atomicAdd (kronmult_gpu/kronmult.cu:126-129).
+template<typename T>
+__device__ __forceinline__ void red_add(T *addr, T v)
+{
+    atomicAdd(addr, v);
+}
+
+__device__ __forceinline__ bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+} // namespace kron

@@ -1,0 +1,371 @@
+// kronmult_b200.cu -- dispatch, C ABI and C++ drop-in entry points of libkronmult_b200.so.
+//
+// Boundary: replaces the host side of the reference's CUDA flavour --
+//   cuda_kronmult_batched<T>      kronmult_gpu/kronmult.cu:173-197  (launcher)
+//   kronmult_batched<double>      kronmult_gpu/kronmult.cu:202-211
+//   kronmult_batched<float>       kronmult_gpu/kronmult.cu:216-224
+//   pow_int                       kronmult_gpu/kronmult.cu:11-15
+// There is no CPU fallback anywhere in this file: if no kernel family accepts a shape the call
+// returns a CUDA error code.
+#include "../../include/kronmult.cuh"
+#include "../../include/kronmult_b200.h"
+#include "common.cuh"
+#include "kernel_generic.cuh"
+#include "kernel_tiny.cuh"
+#include "kernel_regtile.cuh"
+#include "kernel_dmma.cuh"
+
+#include <atomic>
+#include <mutex>
+
+namespace kron
+{
+
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_force{PATH_AUTO};
+static thread_local const char *t_last_path = "none";
+
+struct DeviceInfo
+{
+    int sms        = 0;
+    int smem_optin = 0;
+};
+
+static cudaError_t device_info(DeviceInfo &di)
+{
+    // cached per device ordinal; the reference queries the device on every call (kronmult.cu:185-187)
+    static std::mutex mtx;
+    static DeviceInfo cache[64];
+    static bool have[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mtx);
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!have[dev])
+    {
+        e = cudaDeviceGetAttribute(&cache[dev].sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&cache[dev].smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (e != cudaSuccess) return e;
+        have[dev] = true;
+    }
+    di = cache[dev];
+    return cudaSuccess;
+}
+
+// ----------------------------------------------------------------------------------------------
+// generic path: host-side planning of the passes
+// ----------------------------------------------------------------------------------------------
+template<typename T>
+struct GenericPlan
+{
+    int npass = 0;
+    PassParams<T> pass[8];
+    int smem[8];
+    int grid[8];
+};
+
+static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+template<typename T>
+static bool fill_pass(PassParams<T> &p, int &smem, int &grid, const DeviceInfo &di, long long N, int budget)
+{
+    const int s = (int)sizeof(T);
+    p.tile_elems     = p.Mext * p.LB;
+    p.fibers         = p.tile_elems / p.n;
+    p.lblocks        = (int)(p.L / p.LB);
+    p.tiles_per_item = (N / ((long long)p.Mext * p.L)) * p.lblocks;
+
+    // item streams per CTA: enough fibers for 256 threads, bounded by shared memory
+    int B = (256 + p.fibers - 1) / p.fibers;
+    if (B > 128) B = 128;
+    if (B < 1) B = 1;
+    if (p.tiles_per_item > 1) B = 1;
+    auto bytes = [&](int b, int acc) {
+        int o_acc  = align_up(b * p.tile_elems * s, 16);
+        int o_mats = o_acc + (acc ? align_up(b * p.tile_elems * s, 16) : 0);
+        int o_ptrs = o_mats + align_up(b * p.G * p.n * p.n * s, 16);
+        return o_ptrs + b * (2 + p.G) * 8 + align_up(b * 4, 16);
+    };
+    p.use_acc = p.final_pass ? 1 : 0;
+    while (B > 1 && bytes(B, p.use_acc) > budget) B /= 2;
+    if (bytes(B, p.use_acc) > budget) p.use_acc = 0;
+    if (bytes(B, p.use_acc) > di.smem_optin) return false;
+    p.B        = B;
+    p.off_acc  = align_up(B * p.tile_elems * s, 16);
+    p.off_mats = p.off_acc + (p.use_acc ? align_up(B * p.tile_elems * s, 16) : 0);
+    p.off_ptrs = p.off_mats + align_up(B * p.G * p.n * p.n * s, 16);
+    smem       = bytes(B, p.use_acc);
+
+    // consecutive items per stream: long enough to merge runs of equal outputs, short enough to
+    // leave ~8 work units per SM
+    const long long want_units = (long long)di.sms * 8;
+    long long groups_wanted    = (want_units + p.tiles_per_item - 1) / p.tiles_per_item;
+    if (groups_wanted < 1) groups_wanted = 1;
+    long long chunk = p.nb / ((long long)B * groups_wanted);
+    if (chunk < 1) chunk = 1;
+    if (chunk > 32) chunk = 32;
+    p.chunk = (int)chunk;
+    const long long group_items = (long long)B * p.chunk;
+    const long long ngroups     = (p.nb + group_items - 1) / group_items;
+    p.units                     = ngroups * p.tiles_per_item;
+    const long long max_grid    = (long long)di.sms * 16;
+    grid                        = (int)(p.units < max_grid ? p.units : max_grid);
+    return true;
+}
+
+template<typename T>
+static cudaError_t plan_generic(GenericPlan<T> &plan, const DeviceInfo &di, int d, int n, const T *const *A, int lda,
+                                T *const *in, T *const *out, int nb)
+{
+    if (n < 1 || n > 32 || d < 0) return cudaErrorInvalidValue;
+    long long N = 1;
+    for (int i = 0; i < d; ++i)
+    {
+        N *= n;
+        if (N >= (1LL << 31)) return cudaErrorInvalidValue; // the reference's int size_input overflows here
+    }
+    const int s = (int)sizeof(T);
+    PassParams<T> base{};
+    base.A = A; base.in = in; base.out = out;
+    base.d = d; base.n = n; base.lda = lda; base.nb = nb;
+
+    const int resident_budget = 96 * 1024;           // two CTAs per SM when the accumulator fits
+    const long long resident_max = (long long)(di.smem_optin - 4096) / s;
+    if (d == 0 || N <= resident_max)
+    {
+        PassParams<T> p = base;
+        p.j0 = 0; p.G = d; p.Mext = (int)N; p.L = 1; p.LB = 1; p.final_pass = 1;
+        int budget = resident_budget;
+        if ((long long)2 * N * s + 4096 > budget) budget = di.smem_optin;
+        if (d == 0) { p.G = 0; p.Mext = 1; }
+        if (!fill_pass(p, plan.smem[0], plan.grid[0], di, N, budget)) return cudaErrorInvalidValue;
+        plan.pass[0] = p;
+        plan.npass   = 1;
+        return cudaSuccess;
+    }
+
+    // multi-pass: groups of factors from the fastest index upwards, 32 KiB tiles
+    const long long cap = (32 * 1024) / s;
+    int done = 0; // factors already covered, counted from the fast end
+    int np   = 0;
+    while (done < d)
+    {
+        if (np >= 8) return cudaErrorInvalidValue;
+        PassParams<T> p = base;
+        long long L = 1;
+        for (int i = 0; i < done; ++i) L *= n;
+        // tile width along the faster, untouched indices: at least 8 elements when available
+        long long lbmin = 1;
+        while (lbmin < 8 && lbmin * n <= L) lbmin *= n;
+        int G = 1;
+        long long M = n;
+        while (done + G < d && M * n * lbmin <= cap) { M *= n; ++G; }
+        long long LB = lbmin;
+        while (LB * n <= L && M * LB * n <= cap) LB *= n;
+        p.j0 = d - done - G; p.G = G; p.Mext = (int)M; p.L = L; p.LB = (int)LB;
+        p.final_pass = (done + G == d) ? 1 : 0;
+        if (!fill_pass(p, plan.smem[np], plan.grid[np], di, N, resident_budget)) return cudaErrorInvalidValue;
+        plan.pass[np++] = p;
+        done += G;
+    }
+    plan.npass = np;
+    return cudaSuccess;
+}
+
+template<typename T, int NT>
+static cudaError_t launch_pass(const PassParams<T> &p, int grid, int smem, cudaStream_t st)
+{
+    auto kfn = kron_pass_kernel<T, NT>;
+    if (smem > 48 * 1024)
+    {
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+    }
+    kfn<<<grid, 256, smem, st>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+template<typename T>
+static cudaError_t run_generic(const DeviceInfo &di, int d, int n, const T *const *A, int lda, T *const *in,
+                               T *const *out, int nb, cudaStream_t st)
+{
+    GenericPlan<T> plan;
+    cudaError_t e = plan_generic<T>(plan, di, d, n, A, lda, in, out, nb);
+    if (e != cudaSuccess) return e;
+    for (int i = 0; i < plan.npass; ++i)
+    {
+        const PassParams<T> &p = plan.pass[i];
+        switch (n)
+        {
+#define KRON_CASE(NN) case NN: e = launch_pass<T, NN>(p, plan.grid[i], plan.smem[i], st); break;
+            KRON_CASE(2) KRON_CASE(3) KRON_CASE(4) KRON_CASE(5) KRON_CASE(6) KRON_CASE(7) KRON_CASE(8) KRON_CASE(9)
+            KRON_CASE(10)
+#undef KRON_CASE
+        default: e = launch_pass<T, 0>(p, plan.grid[i], plan.smem[i], st); break;
+        }
+        if (e != cudaSuccess) return e;
+    }
+    t_last_path = plan.npass > 1 ? "generic-multipass" : "generic";
+    return cudaSuccess;
+}
+
+// ----------------------------------------------------------------------------------------------
+// tiny path
+// ----------------------------------------------------------------------------------------------
+template<typename T, int n, int d>
+static cudaError_t launch_tiny(const T *const *A, int lda, T *const *in, T *const *out, int nb, cudaStream_t st)
+{
+    const int threads = 128;
+    const int grid    = (nb + threads - 1) / threads;
+    kron_tiny_kernel<T, n, d><<<grid, threads, 0, st>>>(A, in, out, lda, nb);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    t_last_path = "tiny";
+    return cudaGetLastError();
+}
+
+// returns cudaErrorNotSupported when the shape is outside the family
+template<typename T>
+static cudaError_t run_tiny(int d, int n, const T *const *A, int lda, T *const *in, T *const *out, int nb,
+                            cudaStream_t st)
+{
+#define KRON_TINY(NN, DD) \
+    if (n == NN && d == DD) return launch_tiny<T, NN, DD>(A, lda, in, out, nb, st);
+    KRON_TINY(2, 1) KRON_TINY(2, 2) KRON_TINY(2, 3) KRON_TINY(2, 4)
+    KRON_TINY(3, 1) KRON_TINY(3, 2)
+    KRON_TINY(4, 1) KRON_TINY(4, 2)
+    KRON_TINY(5, 1) KRON_TINY(6, 1) KRON_TINY(7, 1) KRON_TINY(8, 1) KRON_TINY(9, 1) KRON_TINY(10, 1)
+#undef KRON_TINY
+    return cudaErrorNotSupported;
+}
+
+// ----------------------------------------------------------------------------------------------
+// dispatch
+// ----------------------------------------------------------------------------------------------
+template<typename T>
+static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *in, T *const *out, int nb,
+                            cudaStream_t st)
+{
+    if (nb <= 0) return cudaSuccess; // the reference launches an empty grid (kronmult.cu:191) -> no-op
+    if (d < 0 || n < 1 || lda < n || !A || !in || !out) return cudaErrorInvalidValue;
+    DeviceInfo di;
+    cudaError_t e = device_info(di);
+    if (e != cudaSuccess) return e;
+
+    const int force = g_force.load(std::memory_order_relaxed);
+    if (force == PATH_GENERIC) return run_generic<T>(di, d, n, A, lda, in, out, nb, st);
+    if (force == PATH_TINY)
+    {
+        e = run_tiny<T>(d, n, A, lda, in, out, nb, st);
+        return e == cudaErrorNotSupported ? cudaErrorInvalidValue : e;
+    }
+    if (force == PATH_REGTILE)
+    {
+        e = run_regtile<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
+        return e == cudaErrorNotSupported ? cudaErrorInvalidValue : e;
+    }
+    if (force == PATH_DMMA)
+    {
+        e = run_dmma<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
+        return e == cudaErrorNotSupported ? cudaErrorInvalidValue : e;
+    }
+
+    // automatic: most specialised family first
+    e = run_tiny<T>(d, n, A, lda, in, out, nb, st);
+    if (e != cudaErrorNotSupported) return e;
+    e = run_dmma<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
+    if (e != cudaErrorNotSupported) return e;
+    e = run_regtile<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
+    if (e != cudaErrorNotSupported) return e;
+    return run_generic<T>(di, d, n, A, lda, in, out, nb, st);
+}
+
+template<typename T>
+static int blocking_call(int d, int n, const T *const *A, int lda, T **in, T **out, int nb)
+{
+    // legacy default stream + device-wide synchronisation, as kronmult.cu:191-196
+    cudaError_t e = dispatch<T>(d, n, A, lda, in, out, nb, cudaStreamLegacy);
+    cudaError_t s = cudaDeviceSynchronize();
+    return (int)(e != cudaSuccess ? e : s);
+}
+
+} // namespace kron
+
+// ------------------------------------------------------------------------------------------------
+// C ABI (include/kronmult_b200.h)
+// ------------------------------------------------------------------------------------------------
+extern "C"
+{
+int kronmult_pow_int(int number, int power)
+{
+    int v = 1;
+    for (int i = 0; i < power; ++i) v *= number;
+    return v;
+}
+
+int kronmult_batched_f64(int d, int n, const double *const *A, int lda, double **in, double **out, double **ws,
+                         int nb)
+{
+    (void)ws;
+    return kron::blocking_call<double>(d, n, A, lda, in, out, nb);
+}
+
+int kronmult_batched_f32(int d, int n, const float *const *A, int lda, float **in, float **out, float **ws, int nb)
+{
+    (void)ws;
+    return kron::blocking_call<float>(d, n, A, lda, in, out, nb);
+}
+
+int kronmult_batched_f64_async(int d, int n, const double *const *A, int lda, double **in, double **out,
+                               double **ws, int nb, void *stream)
+{
+    (void)ws;
+    return (int)kron::dispatch<double>(d, n, A, lda, in, out, nb, static_cast<cudaStream_t>(stream));
+}
+
+int kronmult_batched_f32_async(int d, int n, const float *const *A, int lda, float **in, float **out, float **ws,
+                               int nb, void *stream)
+{
+    (void)ws;
+    return (int)kron::dispatch<float>(d, n, A, lda, in, out, nb, static_cast<cudaStream_t>(stream));
+}
+
+const char *kronmult_b200_version(void) { return "kronmult993_b200 0.1 (sm_100a)"; }
+long long kronmult_b200_launch_count(void) { return kron::g_launches.load(); }
+const char *kronmult_b200_last_path(void) { return kron::t_last_path; }
+int kronmult_b200_force_path(int path)
+{
+    if (path < kron::PATH_AUTO || path > kron::PATH_DMMA) return (int)cudaErrorInvalidValue;
+    kron::g_force.store(path);
+    return 0;
+}
+}
+
+// ------------------------------------------------------------------------------------------------
+// C++ drop-in symbols (include/kronmult.cuh): same mangled names as the reference library
+// ------------------------------------------------------------------------------------------------
+__host__ int pow_int(int const number, int const power) { return kronmult_pow_int(number, power); }
+
+template<>
+__host__ cudaError kronmult_batched<double>(int const matrix_count, int const matrix_size,
+                                            double const *const matrix_list_batched[], int const matrix_stride,
+                                            double *input_batched[], double *output_batched[],
+                                            double *workspace_batched[], int const nb_batch)
+{
+    return static_cast<cudaError>(kronmult_batched_f64(matrix_count, matrix_size, matrix_list_batched,
+                                                       matrix_stride, input_batched, output_batched,
+                                                       workspace_batched, nb_batch));
+}
+
+template<>
+__host__ cudaError kronmult_batched<float>(int const matrix_count, int const matrix_size,
+                                           float const *const matrix_list_batched[], int const matrix_stride,
+                                           float *input_batched[], float *output_batched[],
+                                           float *workspace_batched[], int const nb_batch)
+{
+    return static_cast<cudaError>(kronmult_batched_f32(matrix_count, matrix_size, matrix_list_batched,
+                                                       matrix_stride, input_batched, output_batched,
+                                                       workspace_batched, nb_batch));
+}

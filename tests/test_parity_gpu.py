@@ -1,0 +1,163 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Tolerances are BASELINE.json's: relative L2 over EVERY output element <= 1e-12 (fp64) / 1e-5 (fp32)
+(atomics and reassociation reorder the sums).  Cases follow the reference's own tests
+(tests/kronmult_test_gpu.cpp:74-75 toy/small, matrix_stride 67, 5 distinct outputs) and its sweep
+envelope (tests/kronmult_fullbench_gpu.cpp:70-74, n in [2,10], d in [1,6]).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, TOL, golden_files
+from kronmult993_b200 import batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _tol(hp):
+    return TOL[str(np.dtype(hp.dtype))]
+
+
+def _check(kron, oracle_mod, hp, path="auto", expected=None, stream=None):
+    p = batch.from_host(hp, "cuda")
+    kron.run_problem(p, path=path, stream=stream)
+    torch.cuda.synchronize()
+    got = p.out_slab.cpu().numpy()
+    exp = expected if expected is not None else oracle_mod.run(hp, "oracle", threads=1)
+    err = oracle_mod.rel_l2(got, exp)
+    assert np.isfinite(got).all()
+    assert err <= _tol(hp), f"rel-L2 {err:.3e} > {_tol(hp):.0e} (path {kron.last_path()})"
+    return err
+
+
+@pytest.mark.parametrize("path", ["auto", "generic"])
+@pytest.mark.parametrize("fname", golden_files())
+def test_golden_vectors(kron, oracle_mod, fname, path):
+    hp, extra = batch.load_host(os.path.join(GOLDEN, fname))
+    _check(kron, oracle_mod, hp, path, expected=extra["expected"])
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("name", ["toy", "small", "medium"])
+def test_reference_named_cases(kron, oracle_mod, name, dt):
+    """tests/kronmult_bench_gpu.cpp:68-70 at their full batch sizes (4 / 64 / 384 items)."""
+    hp = batch.reference_case(name, dt, "cpu", seed=7).to_host()
+    _check(kron, oracle_mod, hp)
+
+
+def test_reference_large_case_shape(kron, oracle_mod):
+    """n = 8, d = 6 (N = 262144 > shared memory): the multi-pass route, 5 distinct outputs."""
+    hp = batch.reference_case("large", torch.float64, "cpu", seed=8, nb_cap=12).to_host()
+    _check(kron, oracle_mod, hp)
+    assert "multipass" in kron.last_path()
+
+
+SWEEP = [(n, d) for n in range(2, 11) for d in range(1, 7) if n ** d <= 20000]
+
+
+@pytest.mark.parametrize("n,d", SWEEP)
+def test_sweep_envelope_fp64(kron, oracle_mod, n, d):
+    nb = max(3, min(300, 200000 // n ** d))
+    hp = batch.make_problem(d, n, nb, torch.float64, "cpu", seed=n * 10 + d, alias="ref", nb_distinct=5,
+                            matrices="reftest").to_host()
+    _check(kron, oracle_mod, hp)
+
+
+@pytest.mark.parametrize("n,d", [(2, 2), (2, 5), (3, 4), (4, 3), (4, 4), (4, 5), (4, 6), (6, 3), (8, 2), (8, 4), (10, 3)])
+def test_sweep_envelope_fp32(kron, oracle_mod, n, d):
+    nb = max(3, min(300, 200000 // n ** d))
+    hp = batch.make_problem(d, n, nb, torch.float32, "cpu", seed=n * 10 + d, alias="runs", items_per_output=3,
+                            lda=n + 3).to_host()
+    _check(kron, oracle_mod, hp)
+
+
+@pytest.mark.parametrize("path,n,d", [("tiny", 2, 2), ("tiny", 4, 2), ("tiny", 3, 2), ("tiny", 9, 1),
+                                      ("regtile", 4, 4), ("regtile", 4, 5), ("regtile", 4, 6),
+                                      ("generic", 4, 5), ("generic", 2, 2), ("generic", 8, 4)])
+@pytest.mark.parametrize("alias,kw", [("distinct", {}), ("runs", dict(items_per_output=32)),
+                                      ("shuffled", dict(items_per_output=5)), ("ref", dict(nb_distinct=1))])
+def test_every_kernel_family_every_aliasing(kron, oracle_mod, path, n, d, alias, kw):
+    """All output pointers equal (`ref`, 1 distinct) is the worst contention case."""
+    N = n ** d
+    nb = max(70, min(3000, 600000 // N))
+    hp = batch.make_problem(d, n, nb, torch.float64, "cpu", seed=3, alias=alias, **kw).to_host()
+    _check(kron, oracle_mod, hp, path)
+    assert kron.last_path().startswith(path)
+
+
+@pytest.mark.parametrize("n,d", [(2, 2), (4, 5), (4, 6), (5, 3), (8, 4)])
+def test_unaligned_vectors_and_strided_matrices(kron, oracle_mod, n, d):
+    """The API only guarantees alignment to T: shift every slab by one element, lda = 67."""
+    for dt in (torch.float64, torch.float32):
+        hp = batch.make_problem(d, n, 37, dt, "cpu", seed=11, alias="runs", items_per_output=4, lda=67,
+                                misalign=1).to_host()
+        _check(kron, oracle_mod, hp)
+
+
+def test_partially_overlapping_outputs(kron, oracle_mod):
+    """The reference is correct for ANY overlap because every add is atomic (kronmult.cu:126-129)."""
+    for (n, d) in [(2, 2), (4, 4), (4, 5), (3, 3)]:
+        N = n ** d
+        p = batch.make_problem(d, n, 40, torch.float64, "cpu", seed=13, alias="distinct")
+        hp = p.to_host()
+        hp.out_off = (np.arange(40, dtype=np.int64) * (N // 2)) % (hp.out_slab.size - N)  # half-vector steps
+        _check(kron, oracle_mod, hp)
+
+
+def test_edge_batches(kron, oracle_mod):
+    hp = batch.make_problem(3, 4, 1, torch.float64, "cpu", seed=1).to_host()
+    _check(kron, oracle_mod, hp)
+    # nb = 0 is a no-op that returns success (kronmult.cu:191-196 launches an empty grid)
+    p = batch.from_host(hp, "cuda")
+    before = p.out_slab.clone()
+    A, i, o, w = p.pointer_arrays()
+    kron.kronmult_batched(3, 4, A, p.lda, i, o, w, 0)
+    assert torch.equal(before, p.out_slab)
+    # workspace may be NULL here
+    kron.kronmult_batched(3, 4, A, p.lda, i, o, None, 1)
+    # a d = 0 "product" is the identity on a length-1 vector
+    hp0 = batch.make_problem(0, 3, 9, torch.float64, "cpu", seed=2, alias="runs", items_per_output=3).to_host()
+    exp = hp0.out_slab.copy()
+    np.add.at(exp, hp0.out_off, hp0.in_slab[hp0.in_off])
+    _check(kron, oracle_mod, hp0, expected=exp)
+
+
+def test_invalid_arguments_return_cuda_errors(kron):
+    p = batch.make_problem(2, 2, 4, torch.float64, "cuda", seed=1)
+    A, i, o, w = p.pointer_arrays()
+    with pytest.raises(kron.KronmultError):
+        kron.kronmult_batched(2, 2, A, 1, i, o, w, 4)  # lda < n
+    with pytest.raises(kron.KronmultError):
+        kron.kronmult_batched(40, 2, A, 2, i, o, w, 4)  # 2^40 overflows the reference's int size_input
+    with pytest.raises(TypeError):
+        kron.kronmult_batched(2, 2, A, 2, i, o, w, 4, dtype=torch.float16)  # only float/double exist
+
+
+def test_stream_ordered_entry(kron, oracle_mod):
+    hp = batch.make_problem(5, 4, 300, torch.float64, "cpu", seed=21, alias="runs", items_per_output=8).to_host()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        _check(kron, oracle_mod, hp, stream=s)
+
+
+def test_large_batch_tiny_items(kron, oracle_mod):
+    """1 Mi items of n = 2, d = 2 (1/16 of BASELINE config 2) against the oracle, every element."""
+    hp = batch.make_problem(2, 2, 1 << 20, torch.float64, "cpu", seed=31).to_host()
+    _check(kron, oracle_mod, hp)
+    assert kron.last_path() == "tiny"
+
+
+def test_repeated_calls_accumulate(kron, oracle_mod):
+    """output += ...: two calls add the product twice (the resident paths never clobber the input)."""
+    hp = batch.make_problem(6, 4, 70, torch.float64, "cpu", seed=41, alias="runs", items_per_output=32).to_host()
+    p = batch.from_host(hp, "cuda")
+    out0 = p.out_slab.clone()
+    kron.run_problem(p)
+    once = p.out_slab.clone()
+    kron.run_problem(p)
+    twice = p.out_slab
+    d1, d2 = (once - out0), (twice - out0)
+    assert float(torch.linalg.norm(d2 - 2 * d1) / torch.linalg.norm(d1)) < 1e-13

@@ -1,0 +1,77 @@
+"""Kernel-only timing of every BASELINE.json configuration on one GPU (development tool).
+
+Prints one JSON line per configuration: CUDA-event time of the stream-ordered C-ABI call, GFLOP/s,
+algorithmic GB/s and the fraction of the applicable roofline (HBM from MEASURED_PEAKS.json, FP peak
+from --fp64-tflops / --fp32-tflops).  bench.py is the graded benchmark; this is for iteration.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from kronmult993_b200 import api, batch  # noqa: E402
+
+CONFIGS = {
+    "c1": (3, 4, 65536, torch.float64, 1),
+    "c2": (2, 2, 1 << 24, torch.float64, 1),
+    "c3": (6, 4, 1 << 20, torch.float64, 32),
+    "c4a": (4, 8, 1 << 19, torch.float64, 1),
+    "c4b": (4, 8, 1 << 19, torch.float64, 32),
+    "c5_f64": (5, 4, 1 << 23, torch.float64, 32),
+    "c5_f32": (5, 4, 1 << 23, torch.float32, 32),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="c2,c3,c4a,c4b,c5_f64,c5_f32,c1")
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the batch")
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--path", default="auto")
+    ap.add_argument("--fp64-tflops", type=float, default=37.0)
+    ap.add_argument("--fp32-tflops", type=float, default=75.0)
+    ap.add_argument("--alias", default=None)
+    args = ap.parse_args()
+    hbm = 6552.3
+    mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(mp):
+        hbm = json.load(open(mp)).get("hbm_gbs", hbm)
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream()
+    for name in args.configs.split(","):
+        d, n, nb, dt, r = CONFIGS[name]
+        nb = max(1, int(nb * args.scale))
+        alias = args.alias or ("runs" if r > 1 else "distinct")
+        p = batch.make_problem(d, n, nb, dt, "cuda", seed=993, alias=alias, items_per_output=r)
+        A, i, o, w = p.pointer_arrays()
+        api.force_path(args.path)
+        times = []
+        with torch.cuda.stream(stream):
+            for rep in range(args.reps + 2):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                api.kronmult_batched(p.d, p.n, A, p.lda, i, o, w, p.nb, dtype=dt, stream=stream)
+                e1.record(stream)
+                e1.synchronize()
+                if rep >= 2:
+                    times.append(e0.elapsed_time(e1))
+        api.force_path("auto")
+        t = min(times) * 1e-3
+        fl, by = p.flops(), p.algorithmic_bytes()
+        peak = (args.fp64_tflops if dt == torch.float64 else args.fp32_tflops) * 1e12
+        roof = max(by / (hbm * 1e9), fl / peak)
+        print(json.dumps({"config": name, "path": api.last_path(), "nb": nb, "ms": round(t * 1e3, 4),
+                          "ms_all": [round(x, 4) for x in times], "gflops": round(fl / t * 1e-9, 1),
+                          "alg_gbs": round(by / t * 1e-9, 1), "roofline_ms": round(roof * 1e3, 4),
+                          "frac": round(roof / t, 4), "bound": "hbm" if by / (hbm * 1e9) >= fl / peak else "fp"}),
+              flush=True)
+        del p, A, i, o, w
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
