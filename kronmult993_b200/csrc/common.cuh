@@ -27,10 +27,15 @@ __host__ __device__ constexpr int ipow(int b, int e)
 // Every final accumulation in this library goes through an atomic-class add so that ANY aliasing of
 // output pointers (equal pointers, partial overlap, non-adjacent repeats) stays correct, like the
 // reference's element-wise atomicAdd (kronmult_gpu/kronmult.cu:126-129).
-template<typename T>
-__device__ __forceinline__ void red_add(T *addr, T v)
+// Output vectors always live in the global address space (device or managed memory, kronmult.cuh:22);
+// saying so in PTX yields REDG instead of a generic ATOM with a shared-memory CAS fallback branch.
+__device__ __forceinline__ void red_add(double *addr, double v)
 {
-    atomicAdd(addr, v);
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void red_add(float *addr, float v)
+{
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 
 __device__ __forceinline__ bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

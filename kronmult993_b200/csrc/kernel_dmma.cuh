@@ -1,13 +1,243 @@
-// kernel_dmma.cuh -- placeholder until the n = 8 FP64 tensor-pipe kernel lands.
+// kernel_dmma.cuh -- n = 8, d = 4, double precision on the FP64 tensor pipe ("dmma" path).
+//
+// Replaces cuda_kronmult_batchelement / cuda_kronmult / multiply_transpose
+// (kronmult_gpu/kronmult.cu:139-167, :95-130, :54-78) for BASELINE config 4 (n = 8, d = 4).
+//
+// tcgen05 has no FP64 kind, so the FP64 tensor path on sm_100a is mma.sync m8n8k4 (SASS DMMA.8x8x4).
+// One mode product with an 8x8 factor M over an 8x8 slice T (contracted index u, other index v) is
+//     D[i][v] = sum_u M[i][u] T[u][v]        = two m8n8k4 steps over u.
+// Fragment layout (lane = 4g+q):  A: M[g][k=q]   B: T[k=q][col=g]   C/D: D[g][2q], D[g][2q+1].
+// Using the contraction order u = 2q+s in step s (A_s = M[g][2q+s], B_s = T[2q+s][g]), a lane's two B
+// values are ADJACENT elements of T (one 128-bit load), and the C/D fragment of this product,
+// D[i=g][v=2q+s], is exactly the B fragment needed to contract v next.  Two factors are therefore
+// chained in registers with no data movement, and the result lands on the same (u in {2q,2q+1},
+// v = g) positions the lane loaded from.  Consequences:
+//   phase 1 (indices i3, i2): each warp loads its 8x8 slices straight from global memory as one
+//           coalesced 512-byte request, chains 4 DMMAs, writes 128-bit to shared memory;
+//   phase 2 (indices i1, i0): slices are strided in memory; a 128-bit shared load fetches the same
+//           (u, v) element of two neighbouring slices, so the warp works on slice pairs; a 16-byte-
+//           chunk XOR swizzle keyed on (i0, i1) makes both phases bank-conflict free;
+//   the factor matrices never touch shared memory (2 doubles per lane per factor), and the last
+//           DMMA accumulates directly onto the running sum of the current run of equal output
+//           pointers (C operand), flushed with RED per element when the pointer changes.
+// Shared-memory traffic is 2 x 32 KiB per item (the reference moves 8 x 32 KiB through GLOBAL memory
+// for d = 4, kronmult.cu:112-121).  Summation order inside a dot product: u even/odd interleaved by
+// the tensor pipe instead of k ascending -- within the 1e-12 relative-L2 tolerance of BASELINE.json.
 #pragma once
 #include "common.cuh"
+#include "kernel_regtile.cuh" // prefetch_l2
 #include <atomic>
+
 namespace kron
 {
-template<typename T>
-static cudaError_t run_dmma(int, int, int, const T *const *, int, T *const *, T *const *, int, cudaStream_t,
-                            std::atomic<long long> &, const char *&)
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b, double c0, double c1)
 {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+        : "=d"(d0), "=d"(d1)
+        : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
+
+// 16-byte-chunk swizzle of the exchange buffer: slice h = i0*8+i1 holds 64 contiguous doubles
+// (32 chunks); chunk index is XORed with ((i0&1)<<2 | i1>>1).
+__device__ __forceinline__ int dmma_sigma(int h) { return (((h >> 3) & 1) << 2) | ((h >> 1) & 3); }
+
+struct Dmma84
+{
+    static constexpr int N       = 4096;
+    static constexpr int WARPS   = 4;               // warps cooperating on one item
+    static constexpr int THREADS = WARPS * 32;
+    static constexpr int T1      = 64 / WARPS;      // phase-1 slices per warp
+    static constexpr int P2      = 32 / WARPS;      // phase-2 slice pairs per warp
+    static constexpr int SMEM    = 2 * N * 8;       // double-buffered exchange
+};
+
+__global__ void __launch_bounds__(Dmma84::THREADS, 3)
+kron_dmma84_kernel(const double *const *__restrict__ A, double *const *__restrict__ in, double *const *__restrict__ out,
+                   const int lda, const int nb, const int chunk)
+{
+    using C = Dmma84;
+    constexpr int N = C::N, T1 = C::T1, P2 = C::P2;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *E = reinterpret_cast<double *>(smem_raw); // [2][4096]
+
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+    const int g = lane >> 2, q = lane & 3;
+
+    double acc[P2][4];
+#pragma unroll
+    for (int j = 0; j < P2; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
+
+    const long long ngroups = (nb + (long long)chunk - 1) / chunk;
+    for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x)
+    {
+        const long long k0   = grp * chunk;
+        const long long kend = (k0 + chunk < nb) ? k0 + chunk : nb;
+
+        // software pipeline over items: factor fragments one item ahead, their pointers two ahead
+        const int lane_off0 = g + (2 * q) * lda; // M[g][2q]; M[g][2q+1] is lda further
+        const double *ap[4];
+        double a_nxt[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+            const double *p0 = A[k0 * 4 + j];
+            a_nxt[2 * j]     = __ldg(p0 + lane_off0);
+            a_nxt[2 * j + 1] = __ldg(p0 + lane_off0 + lda);
+            ap[j]            = (k0 + 1 < kend) ? A[(k0 + 1) * 4 + j] : nullptr;
+        }
+        // L2 prefetch of the first two items (256 lines of 128 B per item, 2 per thread)
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+            if (k0 + a < kend)
+            {
+                const double *ip = in[k0 + a];
+                prefetch_l2(ip + t * 16);
+                prefetch_l2(ip + (t + 128) * 16);
+            }
+        double *o_cur = out[k0];
+        __syncthreads(); // previous group's phase-2 readers are done with both exchange buffers
+
+        for (long long k = k0; k < kend; ++k)
+        {
+            const int cur = (int)((k - k0) & 1);
+            double *Ec    = E + cur * N;
+            double a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = a_nxt[i];
+            if (k + 1 < kend)
+            {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                {
+                    a_nxt[2 * j]     = __ldg(ap[j] + lane_off0);
+                    a_nxt[2 * j + 1] = __ldg(ap[j] + lane_off0 + lda);
+                }
+                if (k + 2 < kend)
+                {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) ap[j] = A[(k + 2) * 4 + j];
+                    const double *ip2 = in[k + 2];
+                    prefetch_l2(ip2 + t * 16);
+                    prefetch_l2(ip2 + (t + 128) * 16);
+                }
+            }
+
+            // ---------------- phase 1: factors 3 (index i3 = u) and 2 (index i2 = v), from global
+            const double *__restrict__ ip = in[k];
+            const bool vec = aligned16(ip);
+#pragma unroll
+            for (int tt = 0; tt < T1; ++tt)
+            {
+                const int h       = w * T1 + tt;
+                const double *src = ip + h * 64 + g * 8 + 2 * q;
+                double x0, x1;
+                if (vec)
+                {
+                    const double2 v = __ldg(reinterpret_cast<const double2 *>(src));
+                    x0 = v.x; x1 = v.y;
+                }
+                else { x0 = __ldg(src); x1 = __ldg(src + 1); }
+                double y0, y1, z0, z1;
+                dmma884(y0, y1, a[6], x0, 0.0, 0.0);
+                dmma884(y0, y1, a[7], x1, y0, y1);
+                dmma884(z0, z1, a[4], y0, 0.0, 0.0);
+                dmma884(z0, z1, a[5], y1, z0, z1);
+                const int chunk16 = (4 * g + q) ^ dmma_sigma(h);
+                *reinterpret_cast<double2 *>(Ec + h * 64 + chunk16 * 2) = make_double2(z0, z1);
+            }
+            __syncthreads();
+
+            // ---------------- phase 2: factors 1 (index i1 = u) and 0 (index i0 = v), slice pairs
+#pragma unroll
+            for (int jj = 0; jj < P2; ++jj)
+            {
+                const int j   = w * P2 + jj; // slices f = 2j, 2j+1
+                const int h0  = g * 8 + 2 * q;
+                const int sg  = ((g & 1) << 2) | q; // dmma_sigma(h0) == dmma_sigma(h0+1)
+                const double2 v0 = *reinterpret_cast<const double2 *>(Ec + h0 * 64 + ((j ^ sg) << 1));
+                const double2 v1 = *reinterpret_cast<const double2 *>(Ec + (h0 + 1) * 64 + ((j ^ sg) << 1));
+                double y0, y1;
+                dmma884(y0, y1, a[2], v0.x, 0.0, 0.0);
+                dmma884(y0, y1, a[3], v1.x, y0, y1);
+                dmma884(acc[jj][0], acc[jj][1], a[0], y0, acc[jj][0], acc[jj][1]);
+                dmma884(acc[jj][0], acc[jj][1], a[1], y1, acc[jj][0], acc[jj][1]);
+                dmma884(y0, y1, a[2], v0.y, 0.0, 0.0);
+                dmma884(y0, y1, a[3], v1.y, y0, y1);
+                dmma884(acc[jj][2], acc[jj][3], a[0], y0, acc[jj][2], acc[jj][3]);
+                dmma884(acc[jj][2], acc[jj][3], a[1], y1, acc[jj][2], acc[jj][3]);
+            }
+
+            double *o_next = (k + 1 < kend) ? out[k + 1] : nullptr;
+            if (o_next != o_cur) // uniform over the CTA
+            {
+                // A lane's sums sit at Out[i0 = g][i1 = 2q + s][f = 2j + t] (acc[jj][s + 2t]): addresses
+                // 512 B apart across lanes.  128-byte-strided REDs are ~7x slower than coalesced ones
+                // (profiles/microbench_r01.jsonl), so transpose through the exchange buffer first: each
+                // warp overwrites exactly the elements it alone read in phase 2 (no barrier needed
+                // before), then the CTA reads the item linearly and issues sector-complete REDs.
+#pragma unroll
+                for (int jj = 0; jj < P2; ++jj)
+                {
+                    const int j  = w * P2 + jj;
+                    const int h0 = g * 8 + 2 * q;
+                    const int sg = ((g & 1) << 2) | q;
+                    *reinterpret_cast<double2 *>(Ec + h0 * 64 + ((j ^ sg) << 1))       = make_double2(acc[jj][0], acc[jj][2]);
+                    *reinterpret_cast<double2 *>(Ec + (h0 + 1) * 64 + ((j ^ sg) << 1)) = make_double2(acc[jj][1], acc[jj][3]);
+                    acc[jj][0] = acc[jj][1] = acc[jj][2] = acc[jj][3] = 0.0;
+                }
+                __syncthreads();
+#pragma unroll 4
+                for (int i = 0; i < N / 2 / C::THREADS; ++i)
+                {
+                    const int c  = t + i * C::THREADS; // 16-byte chunk of the item, linear order
+                    const int h  = c >> 5;
+                    const double2 v = *reinterpret_cast<const double2 *>(Ec + h * 64 + (((c & 31) ^ dmma_sigma(h)) << 1));
+                    red_add(o_cur + 2 * c, v.x);
+                    red_add(o_cur + 2 * c + 1, v.y);
+                }
+            }
+            o_cur = o_next;
+        }
+    }
+}
+
+static cudaError_t launch_dmma84(int sms, const double *const *A, int lda, double *const *in, double *const *out,
+                                 int nb, cudaStream_t st, std::atomic<long long> &launches)
+{
+    using C = Dmma84;
+    static bool attr_done = false;
+    if (!attr_done)
+    {
+        cudaError_t e = cudaFuncSetAttribute(kron_dmma84_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    long long chunk = nb / ((long long)sms * 3 * 8);
+    if (chunk < 1) chunk = 1;
+    if (chunk > 64) chunk = 64;
+    const long long ngroups  = (nb + chunk - 1) / chunk;
+    const long long max_grid = (long long)sms * 3;
+    const int grid           = (int)(ngroups < max_grid ? ngroups : max_grid);
+    kron_dmma84_kernel<<<grid, C::THREADS, C::SMEM, st>>>(A, in, out, lda, nb, (int)chunk);
+    launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+// cudaErrorNotSupported when the shape or type is outside the family
+template<typename T>
+static cudaError_t run_dmma(int sms, int d, int n, const T *const *A, int lda, T *const *in, T *const *out, int nb,
+                            cudaStream_t st, std::atomic<long long> &launches, const char *&last_path)
+{
+    if constexpr (sizeof(T) == 8)
+    {
+        if (n == 8 && d == 4)
+        {
+            last_path = "dmma";
+            return launch_dmma84(sms, A, lda, in, out, nb, st, launches);
+        }
+    }
     return cudaErrorNotSupported;
 }
+
 } // namespace kron

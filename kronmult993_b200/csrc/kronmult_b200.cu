@@ -73,7 +73,7 @@ static bool fill_pass(PassParams<T> &p, int &smem, int &grid, const DeviceInfo &
 {
     const int s = (int)sizeof(T);
     p.tile_elems     = p.Mext * p.LB;
-    p.fibers         = p.tile_elems / p.n;
+    p.fibers         = p.tile_elems / p.n > 0 ? p.tile_elems / p.n : 1;
     p.lblocks        = (int)(p.L / p.LB);
     p.tiles_per_item = (N / ((long long)p.Mext * p.L)) * p.lblocks;
 
@@ -249,7 +249,7 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
                             cudaStream_t st)
 {
     if (nb <= 0) return cudaSuccess; // the reference launches an empty grid (kronmult.cu:191) -> no-op
-    if (d < 0 || n < 1 || lda < n || !A || !in || !out) return cudaErrorInvalidValue;
+    if (d < 0 || n < 1 || lda < n || (!A && d > 0) || !in || !out) return cudaErrorInvalidValue;
     DeviceInfo di;
     cudaError_t e = device_info(di);
     if (e != cudaSuccess) return e;

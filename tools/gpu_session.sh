@@ -17,6 +17,14 @@ for s in $STEPS; do
       timeout 600 python tools/quickbench.py > gpurun_out/quickbench.jsonl 2> gpurun_out/quickbench.err; echo "quick rc=$?"; cat gpurun_out/quickbench.jsonl ;;
     full)
       timeout 900 python -m pytest tests/test_fullsize_gpu.py -q -m gpu -p no:cacheprovider > gpurun_out/fullsize.log 2>&1; echo "full rc=$?"; tail -5 gpurun_out/fullsize.log ;;
+    ncu)
+      # one full-section capture of the top kernels (small batch: ncu replays each launch ~40x)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:'regtile4|dmma84|tiny' -s 2 -c 2 \
+          -f -o gpurun_out/prof_c3 python tools/quickbench.py --configs c3 --scale 0.05 --reps 1 > gpurun_out/ncu_c3.log 2>&1; echo "ncu c3 rc=$?"
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:'regtile4|dmma84|tiny' -s 2 -c 2 \
+          -f -o gpurun_out/prof_c4b python tools/quickbench.py --configs c4b --scale 0.05 --reps 1 > gpurun_out/ncu_c4b.log 2>&1; echo "ncu c4b rc=$?"
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:'regtile4|dmma84|tiny' -s 2 -c 2 \
+          -f -o gpurun_out/prof_c5 python tools/quickbench.py --configs c5_f64 --scale 0.02 --reps 1 > gpurun_out/ncu_c5.log 2>&1; echo "ncu c5 rc=$?" ;;
     smoke)
       timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -8 gpurun_out/smoke.log ;;
   esac

@@ -49,6 +49,7 @@ def main():
         p = batch.make_problem(d, n, nb, dt, "cuda", seed=993, alias=alias, items_per_output=r)
         A, i, o, w = p.pointer_arrays()
         api.force_path(args.path)
+        torch.cuda.synchronize()  # the problem was built on the default stream
         times = []
         with torch.cuda.stream(stream):
             for rep in range(args.reps + 2):
