@@ -70,6 +70,8 @@ const char *kronmult_b200_last_path(void);
 /* 0 = automatic dispatch; otherwise force a kernel family (see kronmult993_b200/csrc/dispatch.h).
  * Unsupported combinations make the next call return cudaErrorInvalidValue.  For tests. */
 int kronmult_b200_force_path(int path);
+/* development knobs (knob 0: regtile operand staging, 0 = TMA into shared memory, 1 = L1 prefetch). */
+int kronmult_b200_set_tuning(int knob, int value);
 
 #ifdef __cplusplus
 }

@@ -39,6 +39,7 @@ C_SYMBOLS = (
     "kronmult_b200_launch_count",
     "kronmult_b200_last_path",
     "kronmult_b200_force_path",
+    "kronmult_b200_set_tuning",
 )
 # the C++ drop-in symbols of include/kronmult.cuh (same mangling as the reference library)
 CXX_SYMBOLS = (
@@ -172,6 +173,12 @@ def force_path(path: Union[str, int]) -> None:
     code = load_library().kronmult_b200_force_path(PATHS[path] if isinstance(path, str) else int(path))
     if code != 0:
         raise KronmultError(code, "kronmult_b200_force_path")
+
+
+def set_tuning(knob: int, value: int) -> None:
+    code = load_library().kronmult_b200_set_tuning(int(knob), int(value))
+    if code != 0:
+        raise KronmultError(code, "kronmult_b200_set_tuning")
 
 
 def last_path() -> str:

@@ -186,16 +186,19 @@ __device__ __forceinline__ void tile16_apply_acc(const T (&x)[16], const T *Ms, 
 #pragma unroll
         for (int i = 0; i < 4; ++i)
         {
-            T dot = a0 * m[i * 4];
+            T dot = acc[base + i * STRIDE];
+            dot += a0 * m[i * 4];
             dot += a1 * m[i * 4 + 1];
             dot += a2 * m[i * 4 + 2];
             dot += a3 * m[i * 4 + 3];
-            acc[base + i * STRIDE] += dot;
+            acc[base + i * STRIDE] = dot;
         }
     }
 }
 
-template<typename T, int D>
+// STAGE = 0: operands of the next step arrive by TMA (or element-wise cp.async) in the other item buffer.
+// STAGE = 1: they are prefetched into L1 (prefetch.global.L1) and phase A loads them from global.
+template<typename T, int D, int STAGE>
 __global__ void __launch_bounds__(Regtile4<T, D>::THREADS, Regtile4<T, D>::MINB)
 kron_regtile4_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T *const *__restrict__ out,
                      const int lda, const int nb, const int chunk, const long long ngroups)
@@ -254,14 +257,26 @@ kron_regtile4_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, 
 
         // does step s exist for this CTA?  (uniform: stream 0 holds the smallest item index)
         auto step_exists = [&](int s) { return s < chunk && g0 + s < nb; };
-        // asynchronous fetch of the operands of step s into item buffer s&1
-        auto stage_data = [&](int s) {
+        // asynchronous fetch of the operands of step s (vector pointer ip, may be null) into item buffer s&1
+        auto stage_data = [&](int s, const T *ip) {
             if (!step_exists(s)) return;
-            const long long k = k0 + s;
-            const bool v      = k < kend;
-            const T *ip       = v ? in[k] : nullptr;
-            const bool tma    = v && aligned16(ip);
-            T *dst            = S + (s & 1) * (B * N) + b * N;
+            const bool v = ip != nullptr;
+            if constexpr (STAGE == 1)
+            {
+                if (v)
+                {
+#pragma unroll
+                    for (int i = 0; i < (N * (int)sizeof(T) / 128 + TPI - 1) / TPI; ++i)
+                    {
+                        const int line = tl + i * TPI;
+                        if (line < N * (int)sizeof(T) / 128)
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(ip + line * (128 / (int)sizeof(T))));
+                    }
+                }
+                return;
+            }
+            const bool tma = v && aligned16(ip);
+            T *dst         = S + (s & 1) * (B * N) + b * N;
             if (tl == 0)
             {
                 if (tma)
@@ -280,15 +295,22 @@ kron_regtile4_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, 
                     for (int h = 0; h < AT; ++h) cp_async_elem<T>(dst + h * R + tl + q * TPI, ip + h * R + tl + q * TPI);
             }
         };
-        auto stage_mats = [&](int s) {
+        // factor elements of step s: ap[q] = pointer to the factor this thread copies from (may be null)
+        auto stage_mats = [&](int s, const T *const (&ap)[LD]) {
             if (!step_exists(s)) return;
-            const long long k = k0 + s;
-            if (k < kend)
-            {
 #pragma unroll
-                for (int q = 0; q < LD; ++q)
-                    if (l_ok[q]) cp_async_elem<T>(MS + (s % NMB) * (B * MSTR) + l_dst[q], A[k * D + l_j[q]] + l_src[q]);
-            }
+            for (int q = 0; q < LD; ++q)
+                if (l_ok[q] && ap[q]) cp_async_elem<T>(MS + (s % NMB) * (B * MSTR) + l_dst[q], ap[q] + l_src[q]);
+        };
+        auto load_in_ptr = [&](int s) -> const T * {
+            const long long k = k0 + s;
+            return (s < chunk && k < kend) ? in[k] : nullptr;
+        };
+        auto load_mat_ptrs = [&](int s, const T *(&ap)[LD]) {
+            const long long k = k0 + s;
+            const bool v      = s < chunk && k < kend;
+#pragma unroll
+            for (int q = 0; q < LD; ++q) ap[q] = (v && l_ok[q]) ? A[k * D + l_j[q]] : nullptr;
         };
         auto l2_prefetch = [&](int s) {
             if (t < C::LPS && s < chunk)
@@ -301,9 +323,13 @@ kron_regtile4_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, 
         __syncthreads(); // the previous group's readers are done with S and MS; mbarriers initialised
 #pragma unroll
         for (int a = 0; a < PFD; ++a) l2_prefetch(a);
-        stage_data(0);
-        stage_mats(0);
-        stage_mats(1);
+        const T *ap_n[LD];
+        const T *ip_cur = load_in_ptr(0);
+        stage_data(0, ip_cur);
+        load_mat_ptrs(0, ap_n);
+        stage_mats(0, ap_n);
+        load_mat_ptrs(1, ap_n);
+        stage_mats(1, ap_n);
         cp_async_commit();
         T *o_cur = (k0 < kend) ? out[k0] : nullptr;
         cp_async_wait_all();
@@ -318,16 +344,30 @@ kron_regtile4_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, 
             T *Sc             = S + cur * (B * N);
             const T *Mc       = MS + (s % NMB) * (B * MSTR) + b * MSTR;
             l2_prefetch(s + PFD);
+            // pointers needed after the barrier are fetched now, so their latency hides behind phase A
+            const T *ip_n = load_in_ptr(s + 1);
+            load_mat_ptrs(s + 2, ap_n);
+            T *o_next = (valid && k + 1 < kend) ? out[k + 1] : nullptr;
 
             // ---------------- phase A: slowest index/indices; linear in, swizzled out, in place per warp
             cp_async_wait_all();                 // element-wise copies issued by this thread during step s-1
-            if (cur == 0) { mbar_wait(bar + 0, parity0); parity0 ^= 1; }
-            else          { mbar_wait(bar + 1, parity1); parity1 ^= 1; }
             T x[16];
+            if constexpr (STAGE == 0)
+            {
+                if (cur == 0) { mbar_wait(bar + 0, parity0); parity0 ^= 1; }
+                else          { mbar_wait(bar + 1, parity1); parity1 ^= 1; }
 #pragma unroll
-            for (int q = 0; q < FA; ++q)
+                for (int q = 0; q < FA; ++q)
 #pragma unroll
-                for (int h = 0; h < AT; ++h) x[q * AT + h] = Sc[b * N + h * R + tl + q * TPI];
+                    for (int h = 0; h < AT; ++h) x[q * AT + h] = Sc[b * N + h * R + tl + q * TPI];
+            }
+            else
+            {
+#pragma unroll
+                for (int q = 0; q < FA; ++q)
+#pragma unroll
+                    for (int h = 0; h < AT; ++h) x[q * AT + h] = valid ? ip_cur[h * R + tl + q * TPI] : T(0);
+            }
             if constexpr (AD == 2)
             {
                 tile16_apply<T, 1>(x, Mc + 1 * 16); // factor 1 acts on the low two bits of h
@@ -345,9 +385,10 @@ kron_regtile4_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, 
             if constexpr (TPI <= 16) __syncwarp();
             else __syncthreads();
 
-            stage_data(s + 1);
-            stage_mats(s + 2);
+            stage_data(s + 1, ip_n);
+            stage_mats(s + 2, ap_n);
             cp_async_commit();
+            ip_cur = ip_n;
 
             // ---------------- phase B: two fastest indices, row-wise 128-bit, in place
             {
@@ -395,7 +436,6 @@ kron_regtile4_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, 
             }
             if (valid)
             {
-                T *o_next = (k + 1 < kend) ? out[k + 1] : nullptr;
                 if (o_next != o_cur)
                 {
                     T *dst = o_cur + (tl / 16) * 256 + (tl % 16);
@@ -412,12 +452,12 @@ kron_regtile4_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, 
     }
 }
 
-template<typename T, int D>
+template<typename T, int D, int STAGE>
 static cudaError_t launch_regtile4(int sms, const T *const *A, int lda, T *const *in, T *const *out, int nb,
                                    cudaStream_t st, std::atomic<long long> &launches)
 {
     using C  = Regtile4<T, D>;
-    auto kfn = kron_regtile4_kernel<T, D>;
+    auto kfn = kron_regtile4_kernel<T, D, STAGE>;
     static bool attr_done = false; // benign race: the attribute call is idempotent
     if (!attr_done)
     {
@@ -438,6 +478,9 @@ static cudaError_t launch_regtile4(int sms, const T *const *A, int lda, T *const
     return cudaGetLastError();
 }
 
+// experiment knob (kronmult_b200_set_tuning): operand staging mode of the regtile kernels
+static std::atomic<int> g_regtile_stage{0};
+
 // cudaErrorNotSupported when (n, d) is outside the family
 template<typename T>
 static cudaError_t run_regtile(int sms, int d, int n, const T *const *A, int lda, T *const *in, T *const *out,
@@ -445,9 +488,14 @@ static cudaError_t run_regtile(int sms, int d, int n, const T *const *A, int lda
 {
     if (n != 4 || d < 4 || d > 6) return cudaErrorNotSupported;
     cudaError_t e;
-    if (d == 4) e = launch_regtile4<T, 4>(sms, A, lda, in, out, nb, st, launches);
-    else if (d == 5) e = launch_regtile4<T, 5>(sms, A, lda, in, out, nb, st, launches);
-    else e = launch_regtile4<T, 6>(sms, A, lda, in, out, nb, st, launches);
+    const int stage = g_regtile_stage.load(std::memory_order_relaxed);
+#define KRON_RT(DD)                                                                              \
+    (stage == 1 ? launch_regtile4<T, DD, 1>(sms, A, lda, in, out, nb, st, launches)              \
+                : launch_regtile4<T, DD, 0>(sms, A, lda, in, out, nb, st, launches))
+    if (d == 4) e = KRON_RT(4);
+    else if (d == 5) e = KRON_RT(5);
+    else e = KRON_RT(6);
+#undef KRON_RT
     last_path = "regtile";
     return e;
 }

@@ -335,6 +335,11 @@ int kronmult_batched_f32_async(int d, int n, const float *const *A, int lda, flo
 const char *kronmult_b200_version(void) { return "kronmult993_b200 0.1 (sm_100a)"; }
 long long kronmult_b200_launch_count(void) { return kron::g_launches.load(); }
 const char *kronmult_b200_last_path(void) { return kron::t_last_path; }
+int kronmult_b200_set_tuning(int knob, int value)
+{
+    if (knob == 0) { kron::g_regtile_stage.store(value); return 0; }
+    return (int)cudaErrorInvalidValue;
+}
 int kronmult_b200_force_path(int path)
 {
     if (path < kron::PATH_AUTO || path > kron::PATH_DMMA) return (int)cudaErrorInvalidValue;

@@ -25,6 +25,11 @@ for s in $STEPS; do
           -f -o gpurun_out/prof_c4b python tools/quickbench.py --configs c4b --scale 0.05 --reps 1 > gpurun_out/ncu_c4b.log 2>&1; echo "ncu c4b rc=$?"
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:'regtile4|dmma84|tiny' -s 2 -c 2 \
           -f -o gpurun_out/prof_c5 python tools/quickbench.py --configs c5_f64 --scale 0.02 --reps 1 > gpurun_out/ncu_c5.log 2>&1; echo "ncu c5 rc=$?" ;;
+    tune)
+      for tv in 0=0 0=1; do echo "tune $tv"; timeout 600 python tools/quickbench.py --configs c3,c5_f64,c5_f32 --tune $tv 2>&1 | tee -a gpurun_out/tune.jsonl; done ;;
+    bench)
+      timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+      timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_ref.json ;;
     smoke)
       timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -8 gpurun_out/smoke.log ;;
   esac

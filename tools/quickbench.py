@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--fp64-tflops", type=float, default=37.0)
     ap.add_argument("--fp32-tflops", type=float, default=75.0)
     ap.add_argument("--alias", default=None)
+    ap.add_argument("--tune", default=None, help="knob=value[,knob=value] for kronmult_b200_set_tuning")
     args = ap.parse_args()
     hbm = 6552.3
     mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -42,6 +43,10 @@ def main():
         hbm = json.load(open(mp)).get("hbm_gbs", hbm)
     torch.cuda.set_device(0)
     stream = torch.cuda.Stream()
+    if args.tune:
+        for kv in args.tune.split(","):
+            kn, va = kv.split("=")
+            api.set_tuning(int(kn), int(va))
     for name in args.configs.split(","):
         d, n, nb, dt, r = CONFIGS[name]
         nb = max(1, int(nb * args.scale))
