@@ -22,8 +22,9 @@ import torch
 
 from . import build as _build
 
-PATH_AUTO, PATH_GENERIC, PATH_TINY, PATH_REGTILE, PATH_DMMA = 0, 1, 2, 3, 4
-PATHS = {"auto": PATH_AUTO, "generic": PATH_GENERIC, "tiny": PATH_TINY, "regtile": PATH_REGTILE, "dmma": PATH_DMMA}
+PATH_AUTO, PATH_GENERIC, PATH_TINY, PATH_REGTILE, PATH_DMMA, PATH_WSPEC = 0, 1, 2, 3, 4, 5
+PATHS = {"auto": PATH_AUTO, "generic": PATH_GENERIC, "tiny": PATH_TINY, "regtile": PATH_REGTILE, "dmma": PATH_DMMA,
+         "wspec": PATH_WSPEC}
 
 # every symbol include/kronmult_b200.h declares (tests/test_abi.py checks the header against this)
 C_SYMBOLS = (

@@ -14,6 +14,7 @@ enum Path : int
     PATH_TINY    = 2, // one thread per item, everything in registers (n^d <= 16)
     PATH_REGTILE = 3, // register-tiled in-place mode products, compile-time (n,d), n in {3,4,5,6}
     PATH_DMMA    = 4, // n = 8 on the FP64 tensor pipe (mma.sync m8n8k4), double only
+    PATH_WSPEC   = 5, // n = 4, d = 5,6: warp-specialised two-phase kernel with 64-value register tiles
 };
 
 __host__ __device__ constexpr int ipow(int b, int e)

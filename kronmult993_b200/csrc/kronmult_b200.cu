@@ -14,6 +14,7 @@
 #include "kernel_tiny.cuh"
 #include "kernel_regtile.cuh"
 #include "kernel_dmma.cuh"
+#include "kernel_wspec.cuh"
 
 #include <atomic>
 #include <mutex>
@@ -266,6 +267,11 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
         e = run_regtile<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
         return e == cudaErrorNotSupported ? cudaErrorInvalidValue : e;
     }
+    if (force == PATH_WSPEC)
+    {
+        e = run_wspec<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
+        return e == cudaErrorNotSupported ? cudaErrorInvalidValue : e;
+    }
     if (force == PATH_DMMA)
     {
         e = run_dmma<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
@@ -276,6 +282,8 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
     e = run_tiny<T>(d, n, A, lda, in, out, nb, st);
     if (e != cudaErrorNotSupported) return e;
     e = run_dmma<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
+    if (e != cudaErrorNotSupported) return e;
+    e = run_wspec<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
     if (e != cudaErrorNotSupported) return e;
     e = run_regtile<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
     if (e != cudaErrorNotSupported) return e;
@@ -342,7 +350,7 @@ int kronmult_b200_set_tuning(int knob, int value)
 }
 int kronmult_b200_force_path(int path)
 {
-    if (path < kron::PATH_AUTO || path > kron::PATH_DMMA) return (int)cudaErrorInvalidValue;
+    if (path < kron::PATH_AUTO || path > kron::PATH_WSPEC) return (int)cudaErrorInvalidValue;
     kron::g_force.store(path);
     return 0;
 }

@@ -75,7 +75,7 @@ def test_sweep_envelope_fp32(kron, oracle_mod, n, d):
 
 
 @pytest.mark.parametrize("path,n,d", [("tiny", 2, 2), ("tiny", 4, 2), ("tiny", 3, 2), ("tiny", 9, 1),
-                                      ("regtile", 4, 4), ("regtile", 4, 5), ("regtile", 4, 6),
+                                      ("regtile", 4, 4), ("regtile", 4, 5), ("regtile", 4, 6), ("wspec", 4, 5), ("wspec", 4, 6),
                                       ("generic", 4, 5), ("generic", 2, 2), ("generic", 8, 4)])
 @pytest.mark.parametrize("alias,kw", [("distinct", {}), ("runs", dict(items_per_output=32)),
                                       ("shuffled", dict(items_per_output=5)), ("ref", dict(nb_distinct=1))])
