@@ -45,15 +45,17 @@ struct Wspec4
     static constexpr int RPI     = N / 64;                         // rows (of 64 values) per item
     static constexpr int IPS     = 64 / RPI;                       // item streams (slots) per CTA
     static constexpr int PITCH   = 64 + 16 / (int)sizeof(T);       // padded row of E, in elements
+    static constexpr int NE      = (sizeof(T) == 4) ? 2 : 1;       // exchange buffers (fp64: shared memory allows one)
+    static constexpr int MINB    = (sizeof(T) == 4) ? 3 : 2;       // resident CTAs per SM aimed at
     static constexpr int NMB     = 4;                              // factor-matrix ring depth
     static constexpr int MSTR    = D * 16 + 16 / (int)sizeof(T);   // per-item factor block
     static constexpr int MEL     = IPS * D * 16;                   // factor elements per step
     static constexpr int LD      = (MEL + 63) / 64;                // ... per P1 thread
     static constexpr int THREADS = 128;
     static constexpr int IN_EL   = 2 * IPS * N;                    // 2 stages, linear
-    static constexpr int E_EL    = 64 * PITCH;
+    static constexpr int E_EL    = NE * 64 * PITCH;
     static constexpr int MS_EL   = NMB * IPS * MSTR;
-    static constexpr int SMEM    = (IN_EL + E_EL + MS_EL) * (int)sizeof(T) + 64 + 8 * IPS;
+    static constexpr int SMEM    = (IN_EL + E_EL + MS_EL) * (int)sizeof(T) + 8 * (2 + 2 * NE) + 8 * IPS + 16;
     static_assert(D == 5 || D == 6, "wspec covers d = 5, 6");
 };
 
@@ -79,6 +81,27 @@ __device__ __forceinline__ void tile64_apply(T (&x)[64], const T *Ms)
     }
 }
 
+// tile16_apply with the factor already in registers (row-major m[i*4+k])
+template<typename T, int STRIDE>
+__device__ __forceinline__ void tile16_apply_m(T (&x)[16], const T (&m)[16])
+{
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+    {
+        const int base = (STRIDE == 1) ? f * 4 : f;
+        const T a0 = x[base], a1 = x[base + STRIDE], a2 = x[base + 2 * STRIDE], a3 = x[base + 3 * STRIDE];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            T dot = a0 * m[i * 4];
+            dot += a1 * m[i * 4 + 1];
+            dot += a2 * m[i * 4 + 2];
+            dot += a3 * m[i * 4 + 3];
+            x[base + i * STRIDE] = dot;
+        }
+    }
+}
+
 __device__ __forceinline__ void bar_sync_named(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 // OR-reduction of a predicate over the 64 threads of a named barrier
 __device__ __forceinline__ bool bar_or_named(int id, bool pred)
@@ -90,12 +113,12 @@ __device__ __forceinline__ bool bar_or_named(int id, bool pred)
 }
 
 template<typename T, int D>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128, Wspec4<T, D>::MINB)
 kron_wspec4_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T *const *__restrict__ out,
-                   const int lda, const int nb, const long long items_per_cta)
+                   const int lda, const int nb, const long long items_per_cta, const int sms)
 {
     using C = Wspec4<T, D>;
-    constexpr int N = C::N, RPI = C::RPI, IPS = C::IPS, PITCH = C::PITCH, NMB = C::NMB;
+    constexpr int N = C::N, RPI = C::RPI, IPS = C::IPS, PITCH = C::PITCH, NMB = C::NMB, NE = C::NE;
     constexpr int MSTR = C::MSTR, LD = C::LD;
     constexpr int VE = 16 / (int)sizeof(T);
     constexpr unsigned ITEM_BYTES = N * sizeof(T);
@@ -105,8 +128,8 @@ kron_wspec4_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
     T *E           = IN + C::IN_EL;                     // [64][PITCH]   exchange / flush buffer
     T *MS          = E + C::E_EL;                       // [NMB][IPS][MSTR]
     uint64_t *bars = reinterpret_cast<uint64_t *>(MS + C::MS_EL + (C::MS_EL & 1));
-    uint64_t *full_in = bars, *e_full = bars + 2, *e_empty = bars + 3;
-    T **flush_ptr  = reinterpret_cast<T **>(bars + 4);  // [IPS] output pointer of a slot that flushes this step
+    uint64_t *full_in = bars, *e_full = bars + 2, *e_empty = bars + 2 + NE;
+    T **flush_ptr  = reinterpret_cast<T **>(bars + 2 + 2 * NE); // [IPS] output pointer of a slot that flushes this step
 
     // this CTA's items, split into IPS consecutive streams of `len` items (slot q: [K0 + q*len, ...))
     const long long K0 = (long long)blockIdx.x * items_per_cta;
@@ -121,8 +144,7 @@ kron_wspec4_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
     {
         mbar_init(full_in + 0, 1);
         mbar_init(full_in + 1, 1);
-        mbar_init(e_full, 64);
-        mbar_init(e_empty, 64);
+        for (int i = 0; i < NE; ++i) { mbar_init(e_full + i, 64); mbar_init(e_empty + i, 64); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -131,10 +153,13 @@ kron_wspec4_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
         return (s < nsteps && k < K0 + (long long)(slot + 1) * len && k < K1) ? k : -1;
     };
 
-    if (t < 64)
+    // Warp w runs on SM sub-partition w % 4.  Co-resident CTAs (b, b + #SMs, ...) swap the roles of their
+    // warp pairs so that every sub-partition hosts P1 and P2 warps (their instruction mixes differ).
+    const bool swap_roles = ((blockIdx.x / sms) & 1) != 0;
+    if ((t < 64) != swap_roles)
     {
         // =================================================================== P1: slow factors, column-wise
-        const int r = t;
+        const int r = t & 63;
         int l_ok[LD], l_dst[LD], l_src[LD], l_q[LD], l_j[LD];
 #pragma unroll
         for (int i = 0; i < LD; ++i)
@@ -202,7 +227,7 @@ kron_wspec4_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
         cp_async_commit();
         in_ptrs(1, ip_nxt);
         mat_ptrs(1, ap);
-        unsigned par_in0 = 0, par_in1 = 0, par_empty = 1; // the first wait on e_empty passes on a fresh barrier
+        unsigned par_in0 = 0, par_in1 = 0;
 
         for (int s = 0; s < nsteps; ++s)
         {
@@ -222,6 +247,10 @@ kron_wspec4_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
 
             const T *Xs = IN + st * (IPS * N) + r;
             const T *Ms = MS + (s % NMB) * (IPS * MSTR);
+            const int eb = s % NE;          // exchange buffer of this step
+            T *Eb        = E + eb * 64 * PITCH;
+            // parity of the (s / NE)-th use of that buffer; the first use passes on a fresh barrier
+            const unsigned par_empty = ((unsigned)(s / NE) & 1u) ^ 1u;
             if constexpr (D == 6)
             {
                 T x[64]; // x[h], h = (i0, i1, i2)
@@ -230,28 +259,61 @@ kron_wspec4_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
                 tile64_apply<T, 1>(x, Ms + 2 * 16);
                 tile64_apply<T, 4>(x, Ms + 1 * 16);
                 tile64_apply<T, 16>(x, Ms + 0 * 16);
-                mbar_wait(e_empty, par_empty); par_empty ^= 1;
+                mbar_wait(e_empty + eb, par_empty);
 #pragma unroll
-                for (int h = 0; h < 64; ++h) E[h * PITCH + r] = x[h];
+                for (int h = 0; h < 64; ++h) Eb[h * PITCH + r] = x[h];
             }
             else
             {
-                T x[IPS][16]; // x[q][h], h = (i0, i1)
+                // d = 5: a thread takes VE adjacent columns of one slot (128-bit accesses) and only that
+                // slot's two slow factors; fp64 needs two passes to cover the four slots
+                constexpr int TPS = 64 / VE, SPP = 64 / TPS, NPASS = IPS / SPP;
+                const int qloc = r / TPS, cv = (r % TPS) * VE;
+                T x[NPASS][VE][16]; // x[pass][column][h], h = (i0, i1)
 #pragma unroll
-                for (int q = 0; q < IPS; ++q)
+                for (int ps = 0; ps < NPASS; ++ps)
                 {
+                    const int qs  = ps * SPP + qloc;
+                    const T *src = IN + st * (IPS * N) + qs * N + cv;
 #pragma unroll
-                    for (int h = 0; h < 16; ++h) x[q][h] = Xs[q * N + h * 64];
-                    tile16_apply<T, 1>(x[q], Ms + q * MSTR + 1 * 16);
-                    tile16_apply<T, 4>(x[q], Ms + q * MSTR + 0 * 16);
+                    for (int h = 0; h < 16; ++h)
+                    {
+                        if constexpr (sizeof(T) == 8)
+                        {
+                            const double2 w = *reinterpret_cast<const double2 *>(src + h * 64);
+                            x[ps][0][h] = w.x; x[ps][1][h] = w.y;
+                        }
+                        else
+                        {
+                            const float4 w = *reinterpret_cast<const float4 *>(src + h * 64);
+                            x[ps][0][h] = w.x; x[ps][1][h] = w.y; x[ps][2][h] = w.z; x[ps][3][h] = w.w;
+                        }
+                    }
+                    T m1[16], m0[16];
+                    lds16<T>(Ms + qs * MSTR + 1 * 16, m1);
+                    lds16<T>(Ms + qs * MSTR + 0 * 16, m0);
+#pragma unroll
+                    for (int v = 0; v < VE; ++v)
+                    {
+                        tile16_apply_m<T, 1>(x[ps][v], m1);
+                        tile16_apply_m<T, 4>(x[ps][v], m0);
+                    }
                 }
-                mbar_wait(e_empty, par_empty); par_empty ^= 1;
+                mbar_wait(e_empty + eb, par_empty);
 #pragma unroll
-                for (int q = 0; q < IPS; ++q)
+                for (int ps = 0; ps < NPASS; ++ps)
+                {
+                    const int qs = ps * SPP + qloc;
 #pragma unroll
-                    for (int h = 0; h < 16; ++h) E[(q * 16 + h) * PITCH + r] = x[q][h];
+                    for (int h = 0; h < 16; ++h)
+                    {
+                        T *dst = Eb + (qs * 16 + h) * PITCH + cv;
+                        if constexpr (sizeof(T) == 8) *reinterpret_cast<double2 *>(dst) = make_double2(x[ps][0][h], x[ps][1][h]);
+                        else *reinterpret_cast<float4 *>(dst) = make_float4(x[ps][0][h], x[ps][1][h], x[ps][2][h], x[ps][3][h]);
+                    }
+                }
             }
-            mbar_arrive(e_full);
+            mbar_arrive(e_full + eb);
 
 #pragma unroll
             for (int q = 0; q < IPS; ++q) { ip_nxt[q] = ip_n2[q]; }
@@ -262,24 +324,34 @@ kron_wspec4_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
     else
     {
         // =================================================================== P2: fast factors + accumulation, row-wise
-        const int p = t - 64, q = p / RPI, hrow = p % RPI;
+        const int p = t & 63, q = p / RPI, hrow = p % RPI;
         T acc[64];
 #pragma unroll
         for (int i = 0; i < 64; ++i) acc[i] = T(0);
-        unsigned par_full = 0;
         long long kq = item_of(0, q);
         T *o_cur     = (kq >= 0) ? out[kq] : nullptr;
-        T *erow      = E + p * PITCH;
+        kq           = item_of(1, q);
+        T *o_next    = (kq >= 0) ? out[kq] : nullptr; // output pointers are fetched two steps ahead
 
         for (int s = 0; s < nsteps; ++s)
         {
             const long long k  = item_of(s, q);
-            const long long k1 = item_of(s + 1, q);
-            T *o_next = (k1 >= 0) ? out[k1] : nullptr; // consumed at the end of the step
-            mbar_wait(e_full, par_full); par_full ^= 1;
+            const long long k2 = item_of(s + 2, q);
+            T *o_next2 = (k2 >= 0) ? out[k2] : nullptr;
+            const int eb = s % NE;
+            T *Eb        = E + eb * 64 * PITCH;
+            T *erow      = Eb + p * PITCH;
+            mbar_wait(e_full + eb, (unsigned)(s / NE) & 1u);
             const T *Mq = MS + (s % NMB) * (IPS * MSTR) + q * MSTR;
             if (k >= 0)
             {
+                // fp32 has the registers to keep the two fastest factors for the whole row
+                [[maybe_unused]] T mf[16], mg[16];
+                if constexpr (sizeof(T) == 4)
+                {
+                    lds16<T>(Mq + (D - 1) * 16, mf);
+                    lds16<T>(Mq + (D - 2) * 16, mg);
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                 {
@@ -298,8 +370,16 @@ kron_wspec4_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
                             x[4 * c] = w.x; x[4 * c + 1] = w.y; x[4 * c + 2] = w.z; x[4 * c + 3] = w.w;
                         }
                     }
-                    tile16_apply<T, 1>(x, Mq + (D - 1) * 16); // fastest index
-                    tile16_apply<T, 4>(x, Mq + (D - 2) * 16);
+                    if constexpr (sizeof(T) == 4)
+                    {
+                        tile16_apply_m<T, 1>(x, mf);
+                        tile16_apply_m<T, 4>(x, mg);
+                    }
+                    else
+                    {
+                        tile16_apply<T, 1>(x, Mq + (D - 1) * 16); // fastest index
+                        tile16_apply<T, 4>(x, Mq + (D - 2) * 16);
+                    }
                     const T *M3 = Mq + (D - 3) * 16;
                     const T c0 = M3[0 * 4 + j], c1 = M3[1 * 4 + j], c2 = M3[2 * 4 + j], c3 = M3[3 * 4 + j];
 #pragma unroll
@@ -338,12 +418,13 @@ kron_wspec4_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
                     if (dst)
                     {
 #pragma unroll 8
-                        for (int h = 0; h < RPI; ++h) red_add(dst + h * 64 + p, E[(qq * RPI + h) * PITCH + p]);
+                        for (int h = 0; h < RPI; ++h) red_add(dst + h * 64 + p, Eb[(qq * RPI + h) * PITCH + p]);
                     }
                 }
             }
-            mbar_arrive(e_empty); // every read of E and of this step's factors is done
-            o_cur = o_next;
+            mbar_arrive(e_empty + eb); // every read of E and of this step's factors is done
+            o_cur  = o_next;
+            o_next = o_next2;
         }
     }
 }
@@ -371,7 +452,7 @@ static cudaError_t launch_wspec4(int sms, const T *const *A, int lda, T *const *
     const long long align = 32LL * C::IPS;
     if (ipc > 2 * align) ipc = (ipc + align - 1) / align * align;
     grid = ((long long)nb + ipc - 1) / ipc;
-    kfn<<<(int)grid, C::THREADS, C::SMEM, st>>>(A, in, out, lda, nb, ipc);
+    kfn<<<(int)grid, C::THREADS, C::SMEM, st>>>(A, in, out, lda, nb, ipc, sms);
     launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
