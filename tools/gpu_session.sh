@@ -3,7 +3,7 @@
 # Usage (from the repo root, under gpurun): bash tools/gpu_session.sh [steps...]
 #   steps: box micro parity quick full smoke   (default: all)
 mkdir -p gpurun_out
-STEPS="${@:-box micro parity quick full smoke}"
+STEPS="${@:-box micro parity quick full refbin smoke}"
 for s in $STEPS; do
   case $s in
     box)
@@ -30,6 +30,11 @@ for s in $STEPS; do
     bench)
       timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
       timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_ref.json ;;
+    refbin)
+      timeout 300 python -m pytest tests/test_reference_binaries_gpu.py -q -m gpu -p no:cacheprovider 2>&1 | tail -3
+      LD_LIBRARY_PATH=kronmult993_b200 timeout 600 ./oracle/_ref/kronmult_bench_gpu > gpurun_out/ref_bench_gpu_vs_b200.txt 2>&1; echo "ref bench rc=$?"; tail -7 gpurun_out/ref_bench_gpu_vs_b200.txt ;;
+    refgpu)
+      for c in c5_f64 c3 c4b c2; do timeout 600 python bench.py --impl reference_gpu --config $c --steps 3 --warmup 1 2>> gpurun_out/bench.err | tee -a gpurun_out/bench_refgpu.jsonl; done ;;
     smoke)
       timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -8 gpurun_out/smoke.log ;;
   esac
