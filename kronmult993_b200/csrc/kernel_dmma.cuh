@@ -224,17 +224,283 @@ static cudaError_t launch_dmma84(int sms, const double *const *A, int lda, doubl
     return cudaGetLastError();
 }
 
-// cudaErrorNotSupported when the shape or type is outside the family
+
+// ------------------------------------------------------------------------------------------------
+// n = 8, d = 5 and 6 (n^d = 32768 / 262144: the reference's `large`/`realistic` cases,
+// tests/kronmult_bench_gpu.cpp:71-72).  The vector no longer fits on chip, so the factors are applied in two
+// passes through global memory, in place in `input` (which kronmult.cuh:23 allows to be clobbered):
+//   pass A (kron_dmma8_tile4_kernel): the four fastest factors on every contiguous 4096-element tile,
+//          with exactly the two-phase DMMA scheme above, result written back over the tile;
+//   pass B (kron_dmma8_rows2_kernel, d = 6): factors 0 and 1 on 64 x 64 tiles (64 rows = (i0, i1), 64
+//          consecutive columns), fetched with 16-byte cp.async into the chunk-swizzled layout, DMMA phase 2,
+//          accumulated over consecutive items of equal output pointer and flushed with coalesced REDG.
+//          For d = 5 the remaining single factor goes through the generic pass kernel.
+// The reference moves 2 x N x 8 bytes through global memory per FACTOR (kronmult.cu:112-121); this moves
+// 3 x N x 8 bytes per ITEM.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(Dmma84::THREADS, 3)
+kron_dmma8_tile4_kernel(const double *const *__restrict__ A, double *const *__restrict__ in, const int lda,
+                        const int d, const int tiles_per_item, const long long total_units)
+{
+    using C = Dmma84;
+    constexpr int N = C::N, T1 = C::T1, P2 = C::P2;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *E = reinterpret_cast<double *>(smem_raw); // [2][4096]
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int lane_off0 = g + (2 * q) * lda;
+
+    int it = 0;
+    for (long long u = blockIdx.x; u < total_units; u += gridDim.x, ++it)
+    {
+        const long long k = u / tiles_per_item;
+        const int tile    = (int)(u - k * tiles_per_item);
+        double *base      = in[k] + (long long)tile * N;
+        double *Ec        = E + (it & 1) * N;
+        double a[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+            const double *p0 = A[k * d + (d - 4) + j];
+            a[2 * j]     = __ldg(p0 + lane_off0);
+            a[2 * j + 1] = __ldg(p0 + lane_off0 + lda);
+        }
+        const bool vec = aligned16(base);
+        // phase 1: the two fastest indices
+#pragma unroll
+        for (int tt = 0; tt < T1; ++tt)
+        {
+            const int h       = w * T1 + tt;
+            const double *src = base + h * 64 + g * 8 + 2 * q;
+            double x0, x1;
+            if (vec)
+            {
+                const double2 v = *reinterpret_cast<const double2 *>(src);
+                x0 = v.x; x1 = v.y;
+            }
+            else { x0 = src[0]; x1 = src[1]; }
+            double y0, y1, z0, z1;
+            dmma884(y0, y1, a[6], x0, 0.0, 0.0);
+            dmma884(y0, y1, a[7], x1, y0, y1);
+            dmma884(z0, z1, a[4], y0, 0.0, 0.0);
+            dmma884(z0, z1, a[5], y1, z0, z1);
+            const int chunk16 = (4 * g + q) ^ dmma_sigma(h);
+            *reinterpret_cast<double2 *>(Ec + h * 64 + chunk16 * 2) = make_double2(z0, z1);
+        }
+        __syncthreads();
+        // phase 2: the next two indices; results go back to the slots this warp alone read
+#pragma unroll
+        for (int jj = 0; jj < P2; ++jj)
+        {
+            const int j  = w * P2 + jj;
+            const int h0 = g * 8 + 2 * q;
+            const int sg = ((g & 1) << 2) | q;
+            double2 *p0  = reinterpret_cast<double2 *>(Ec + h0 * 64 + ((j ^ sg) << 1));
+            double2 *p1  = reinterpret_cast<double2 *>(Ec + (h0 + 1) * 64 + ((j ^ sg) << 1));
+            const double2 v0 = *p0, v1 = *p1;
+            double y0, y1, r0, r1, r2, r3;
+            dmma884(y0, y1, a[2], v0.x, 0.0, 0.0);
+            dmma884(y0, y1, a[3], v1.x, y0, y1);
+            dmma884(r0, r1, a[0], y0, 0.0, 0.0);
+            dmma884(r0, r1, a[1], y1, r0, r1);
+            dmma884(y0, y1, a[2], v0.y, 0.0, 0.0);
+            dmma884(y0, y1, a[3], v1.y, y0, y1);
+            dmma884(r2, r3, a[0], y0, 0.0, 0.0);
+            dmma884(r2, r3, a[1], y1, r2, r3);
+            *p0 = make_double2(r0, r2);
+            *p1 = make_double2(r1, r3);
+        }
+        __syncthreads();
+        // linear write-back of the tile (coalesced 128-bit stores)
+#pragma unroll 4
+        for (int i = 0; i < N / 2 / C::THREADS; ++i)
+        {
+            const int c  = t + i * C::THREADS;
+            const int h  = c >> 5;
+            const double2 v = *reinterpret_cast<const double2 *>(Ec + h * 64 + (((c & 31) ^ dmma_sigma(h)) << 1));
+            if (vec) *reinterpret_cast<double2 *>(base + 2 * c) = v;
+            else { base[2 * c] = v.x; base[2 * c + 1] = v.y; }
+        }
+        // the other exchange buffer is used next; its readers finished before the second barrier above
+    }
+}
+
+// pass B for d = 6: factors 0 and 1.  L = n^d / 64 columns per row, tile = 64 rows x 64 columns.
+__global__ void __launch_bounds__(Dmma84::THREADS, 3)
+kron_dmma8_rows2_kernel(const double *const *__restrict__ A, double *const *__restrict__ in, double *const *__restrict__ out,
+                        const int lda, const int nb, const int d, const long long L, const int tiles, const int chunk,
+                        const long long total_units)
+{
+    using C = Dmma84;
+    constexpr int N = C::N, P2 = C::P2;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *E = reinterpret_cast<double *>(smem_raw); // [2][4096]
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int lane_off0 = g + (2 * q) * lda;
+
+    double acc[P2][4];
+#pragma unroll
+    for (int j = 0; j < P2; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
+
+    // tile of item k -> swizzled exchange buffer, 16-byte chunks (8-byte elements when unaligned)
+    auto fetch = [&](long long k, int tile, double *Eb) {
+        const double *src = in[k] + (long long)tile * 64;
+        const bool vec    = aligned16(src) && ((L & 1) == 0);
+#pragma unroll 4
+        for (int i = 0; i < N / 2 / C::THREADS; ++i)
+        {
+            const int c = t + i * C::THREADS, h = c >> 5, ci = c & 31;
+            double *dst = Eb + h * 64 + ((ci ^ dmma_sigma(h)) << 1);
+            const double *s2 = src + (long long)h * L + 2 * ci;
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+            if (vec) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(s2) : "memory");
+            else
+            {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(s2) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa + 8), "l"(s2 + 1) : "memory");
+            }
+        }
+        cp_async_commit();
+    };
+
+    for (long long u = blockIdx.x; u < total_units; u += gridDim.x)
+    {
+        const long long c0   = u / tiles;            // item chunk
+        const int tile       = (int)(u - c0 * tiles);
+        const long long k0   = c0 * chunk;
+        const long long kend = (k0 + chunk < nb) ? k0 + chunk : nb;
+        __syncthreads(); // previous unit's readers are done with both buffers
+        fetch(k0, tile, E);
+        double *o_cur = out[k0];
+        for (long long k = k0; k < kend; ++k)
+        {
+            double *Ec = E + (int)((k - k0) & 1) * N;
+            double a[4];
+            {
+                const double *p0 = A[k * d + 0], *p1 = A[k * d + 1];
+                a[0] = __ldg(p0 + lane_off0); a[1] = __ldg(p0 + lane_off0 + lda);
+                a[2] = __ldg(p1 + lane_off0); a[3] = __ldg(p1 + lane_off0 + lda);
+            }
+            double *o_next = (k + 1 < kend) ? out[k + 1] : nullptr;
+            cp_async_wait_all();
+            __syncthreads(); // tile k is visible; everyone left iteration k-1, so the other buffer is free
+            if (k + 1 < kend) fetch(k + 1, tile, E + (int)(((k - k0) & 1) ^ 1) * N);
+#pragma unroll
+            for (int jj = 0; jj < P2; ++jj)
+            {
+                const int j  = w * P2 + jj;
+                const int h0 = g * 8 + 2 * q;
+                const int sg = ((g & 1) << 2) | q;
+                const double2 v0 = *reinterpret_cast<const double2 *>(Ec + h0 * 64 + ((j ^ sg) << 1));
+                const double2 v1 = *reinterpret_cast<const double2 *>(Ec + (h0 + 1) * 64 + ((j ^ sg) << 1));
+                double y0, y1;
+                dmma884(y0, y1, a[2], v0.x, 0.0, 0.0);
+                dmma884(y0, y1, a[3], v1.x, y0, y1);
+                dmma884(acc[jj][0], acc[jj][1], a[0], y0, acc[jj][0], acc[jj][1]);
+                dmma884(acc[jj][0], acc[jj][1], a[1], y1, acc[jj][0], acc[jj][1]);
+                dmma884(y0, y1, a[2], v0.y, 0.0, 0.0);
+                dmma884(y0, y1, a[3], v1.y, y0, y1);
+                dmma884(acc[jj][2], acc[jj][3], a[0], y0, acc[jj][2], acc[jj][3]);
+                dmma884(acc[jj][2], acc[jj][3], a[1], y1, acc[jj][2], acc[jj][3]);
+            }
+            if (o_next != o_cur) // uniform over the CTA
+            {
+#pragma unroll
+                for (int jj = 0; jj < P2; ++jj)
+                {
+                    const int j  = w * P2 + jj;
+                    const int h0 = g * 8 + 2 * q;
+                    const int sg = ((g & 1) << 2) | q;
+                    *reinterpret_cast<double2 *>(Ec + h0 * 64 + ((j ^ sg) << 1))       = make_double2(acc[jj][0], acc[jj][2]);
+                    *reinterpret_cast<double2 *>(Ec + (h0 + 1) * 64 + ((j ^ sg) << 1)) = make_double2(acc[jj][1], acc[jj][3]);
+                    acc[jj][0] = acc[jj][1] = acc[jj][2] = acc[jj][3] = 0.0;
+                }
+                __syncthreads();
+                double *obase = o_cur + (long long)tile * 64;
+#pragma unroll 4
+                for (int i = 0; i < N / 2 / C::THREADS; ++i)
+                {
+                    const int c = t + i * C::THREADS, h = c >> 5, ci = c & 31;
+                    const double2 v = *reinterpret_cast<const double2 *>(Ec + h * 64 + ((ci ^ dmma_sigma(h)) << 1));
+                    red_add(obase + (long long)h * L + 2 * ci, v.x);
+                    red_add(obase + (long long)h * L + 2 * ci + 1, v.y);
+                }
+            }
+            o_cur = o_next;
+        }
+    }
+}
+
+// pass A for n = 8, d >= 5: the four fastest factors, in place
+static cudaError_t launch_dmma8_tile4(int sms, int d, long long N, const double *const *A, int lda, double *const *in,
+                                      int nb, cudaStream_t st, std::atomic<long long> &launches)
+{
+    using C = Dmma84;
+    static bool attr_done = false;
+    if (!attr_done)
+    {
+        cudaError_t e = cudaFuncSetAttribute(kron_dmma8_tile4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const int tpi            = (int)(N / C::N);
+    const long long units    = (long long)nb * tpi;
+    const long long max_grid = (long long)sms * 3;
+    const int grid           = (int)(units < max_grid ? units : max_grid);
+    kron_dmma8_tile4_kernel<<<grid, C::THREADS, C::SMEM, st>>>(A, in, lda, d, tpi, units);
+    launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+// pass B for n = 8, d = 6: factors 0 and 1 with accumulation into the outputs
+static cudaError_t launch_dmma8_rows2(int sms, int d, long long N, const double *const *A, int lda, double *const *in,
+                                      double *const *out, int nb, cudaStream_t st, std::atomic<long long> &launches)
+{
+    using C = Dmma84;
+    static bool attr_done = false;
+    if (!attr_done)
+    {
+        cudaError_t e = cudaFuncSetAttribute(kron_dmma8_rows2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    const long long L = N / 64;
+    const int tiles   = (int)(L / 64);
+    long long chunk   = ((long long)nb * tiles) / ((long long)sms * 12);
+    if (chunk < 1) chunk = 1;
+    if (chunk > 64) chunk = 64;
+    const long long units    = ((nb + chunk - 1) / chunk) * tiles;
+    const long long max_grid = (long long)sms * 3;
+    const int grid           = (int)(units < max_grid ? units : max_grid);
+    kron_dmma8_rows2_kernel<<<grid, C::THREADS, C::SMEM, st>>>(A, in, out, lda, nb, d, L, tiles, (int)chunk, units);
+    launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+// cudaErrorNotSupported when the shape or type is outside the family.
+// d = 5 returns cudaSuccess after pass A with *remaining = 1: the caller applies factor 0 (generic pass).
 template<typename T>
 static cudaError_t run_dmma(int sms, int d, int n, const T *const *A, int lda, T *const *in, T *const *out, int nb,
-                            cudaStream_t st, std::atomic<long long> &launches, const char *&last_path)
+                            cudaStream_t st, std::atomic<long long> &launches, const char *&last_path, int *remaining)
 {
+    *remaining = 0;
     if constexpr (sizeof(T) == 8)
     {
         if (n == 8 && d == 4)
         {
             last_path = "dmma";
             return launch_dmma84(sms, A, lda, in, out, nb, st, launches);
+        }
+        if (n == 8 && (d == 5 || d == 6))
+        {
+            const long long N = (d == 5) ? 32768 : 262144;
+            last_path = "dmma-multipass";
+            cudaError_t e = launch_dmma8_tile4(sms, d, N, A, lda, in, nb, st, launches);
+            if (e != cudaSuccess) return e;
+            if (d == 6) return launch_dmma8_rows2(sms, d, N, A, lda, in, out, nb, st, launches);
+            *remaining = 1;
+            return cudaSuccess;
         }
     }
     return cudaErrorNotSupported;

@@ -129,7 +129,6 @@ kron_wspec4_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
     T *MS          = E + C::E_EL;                       // [NMB][IPS][MSTR]
     uint64_t *bars = reinterpret_cast<uint64_t *>(MS + C::MS_EL + (C::MS_EL & 1));
     uint64_t *full_in = bars, *e_full = bars + 2, *e_empty = bars + 2 + NE;
-    T **flush_ptr  = reinterpret_cast<T **>(bars + 2 + 2 * NE); // [IPS] output pointer of a slot that flushes this step
 
     // this CTA's items, split into IPS consecutive streams of `len` items (slot q: [K0 + q*len, ...))
     const long long K0 = (long long)blockIdx.x * items_per_cta;
@@ -392,34 +391,42 @@ kron_wspec4_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
                     }
                 }
             }
-            // ---- flush the slots whose run of equal output pointers ends here (all P2 threads take part)
-            const bool my_flush = (k >= 0) && (o_next != o_cur);
-            bool any_flush = my_flush; // d = 6: one item per step, uniform over the P2 threads
-            if constexpr (IPS > 1) any_flush = bar_or_named(3, my_flush);
-            if (any_flush)
+            // ---- flush when the run of equal output pointers ends here.  The accumulators go back into the
+            // thread's own row of E (it is the only reader of that row), then the item's threads read E
+            // column-wise so that the REDs of neighbouring lanes are contiguous.
+            const bool my_flush = (k >= 0) && (o_next != o_cur); // uniform over the threads of one item
+            if (my_flush)
             {
+#pragma unroll
+                for (int c = 0; c < 64 / VE; ++c)
+                {
+                    if constexpr (sizeof(T) == 8) *reinterpret_cast<double2 *>(erow + c * VE) = make_double2(acc[2 * c], acc[2 * c + 1]);
+                    else *reinterpret_cast<float4 *>(erow + c * VE) = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+                }
+#pragma unroll
+                for (int i = 0; i < 64; ++i) acc[i] = T(0);
+            }
+            if constexpr (RPI == 64)
+            {
+                // d = 6: the item spans both P2 warps
+                if (my_flush)
+                {
+                    bar_sync_named(2);
+#pragma unroll 8
+                    for (int h = 0; h < 64; ++h) red_add(o_cur + h * 64 + p, Eb[h * PITCH + p]);
+                }
+            }
+            else
+            {
+                // d = 5: the item's 16 rows belong to one aligned half-warp; each thread takes 4 columns
+                __syncwarp();
                 if (my_flush)
                 {
 #pragma unroll
-                    for (int c = 0; c < 64 / VE; ++c)
-                    {
-                        if constexpr (sizeof(T) == 8) *reinterpret_cast<double2 *>(erow + c * VE) = make_double2(acc[2 * c], acc[2 * c + 1]);
-                        else *reinterpret_cast<float4 *>(erow + c * VE) = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 64; ++i) acc[i] = T(0);
-                }
-                if (hrow == 0) flush_ptr[q] = my_flush ? o_cur : nullptr;
-                bar_sync_named(2);
-#pragma unroll
-                for (int qq = 0; qq < IPS; ++qq)
-                {
-                    T *dst = flush_ptr[qq];
-                    if (dst)
-                    {
-#pragma unroll 8
-                        for (int h = 0; h < RPI; ++h) red_add(dst + h * 64 + p, Eb[(qq * RPI + h) * PITCH + p]);
-                    }
+                    for (int cc = 0; cc < 4; ++cc)
+#pragma unroll 4
+                        for (int h = 0; h < 16; ++h)
+                            red_add(o_cur + h * 64 + cc * 16 + hrow, Eb[(q * 16 + h) * PITCH + cc * 16 + hrow]);
                 }
             }
             mbar_arrive(e_empty + eb); // every read of E and of this step's factors is done

@@ -118,7 +118,7 @@ static bool fill_pass(PassParams<T> &p, int &smem, int &grid, const DeviceInfo &
 
 template<typename T>
 static cudaError_t plan_generic(GenericPlan<T> &plan, const DeviceInfo &di, int d, int n, const T *const *A, int lda,
-                                T *const *in, T *const *out, int nb)
+                                T *const *in, T *const *out, int nb, int fast_done = 0)
 {
     if (n < 1 || n > 32 || d < 0) return cudaErrorInvalidValue;
     long long N = 1;
@@ -134,7 +134,7 @@ static cudaError_t plan_generic(GenericPlan<T> &plan, const DeviceInfo &di, int 
 
     const int resident_budget = 96 * 1024;           // two CTAs per SM when the accumulator fits
     const long long resident_max = (long long)(di.smem_optin - 4096) / s;
-    if (d == 0 || N <= resident_max)
+    if (fast_done == 0 && (d == 0 || N <= resident_max))
     {
         PassParams<T> p = base;
         p.j0 = 0; p.G = d; p.Mext = (int)N; p.L = 1; p.LB = 1; p.final_pass = 1;
@@ -149,7 +149,7 @@ static cudaError_t plan_generic(GenericPlan<T> &plan, const DeviceInfo &di, int 
 
     // multi-pass: groups of factors from the fastest index upwards, 32 KiB tiles
     const long long cap = (32 * 1024) / s;
-    int done = 0; // factors already covered, counted from the fast end
+    int done = fast_done; // factors already covered (by an earlier kernel), counted from the fast end
     int np   = 0;
     while (done < d)
     {
@@ -191,10 +191,10 @@ static cudaError_t launch_pass(const PassParams<T> &p, int grid, int smem, cudaS
 
 template<typename T>
 static cudaError_t run_generic(const DeviceInfo &di, int d, int n, const T *const *A, int lda, T *const *in,
-                               T *const *out, int nb, cudaStream_t st)
+                               T *const *out, int nb, cudaStream_t st, int fast_done = 0)
 {
     GenericPlan<T> plan;
-    cudaError_t e = plan_generic<T>(plan, di, d, n, A, lda, in, out, nb);
+    cudaError_t e = plan_generic<T>(plan, di, d, n, A, lda, in, out, nb, fast_done);
     if (e != cudaSuccess) return e;
     for (int i = 0; i < plan.npass; ++i)
     {
@@ -209,7 +209,7 @@ static cudaError_t run_generic(const DeviceInfo &di, int d, int n, const T *cons
         }
         if (e != cudaSuccess) return e;
     }
-    t_last_path = plan.npass > 1 ? "generic-multipass" : "generic";
+    if (fast_done == 0) t_last_path = plan.npass > 1 ? "generic-multipass" : "generic";
     return cudaSuccess;
 }
 
@@ -274,15 +274,21 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
     }
     if (force == PATH_DMMA)
     {
-        e = run_dmma<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
+        int remaining = 0;
+        e = run_dmma<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path, &remaining);
+        if (e == cudaSuccess && remaining > 0) e = run_generic<T>(di, d, n, A, lda, in, out, nb, st, d - remaining);
         return e == cudaErrorNotSupported ? cudaErrorInvalidValue : e;
     }
 
     // automatic: most specialised family first
     e = run_tiny<T>(d, n, A, lda, in, out, nb, st);
     if (e != cudaErrorNotSupported) return e;
-    e = run_dmma<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
-    if (e != cudaErrorNotSupported) return e;
+    {
+        int remaining = 0;
+        e = run_dmma<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path, &remaining);
+        if (e == cudaSuccess && remaining > 0) e = run_generic<T>(di, d, n, A, lda, in, out, nb, st, d - remaining);
+        if (e != cudaErrorNotSupported) return e;
+    }
     e = run_wspec<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
     if (e != cudaErrorNotSupported) return e;
     e = run_regtile<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);

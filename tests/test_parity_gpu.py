@@ -53,6 +53,16 @@ def test_reference_large_case_shape(kron, oracle_mod):
     hp = batch.reference_case("large", torch.float64, "cpu", seed=8, nb_cap=12).to_host()
     _check(kron, oracle_mod, hp)
     assert "multipass" in kron.last_path()
+    _check(kron, oracle_mod, hp, "generic")  # the shape-agnostic multi-pass route must agree too
+    assert kron.last_path() == "generic-multipass"
+
+
+@pytest.mark.parametrize("n,d,nb", [(8, 5, 40), (8, 6, 7), (7, 6, 5), (10, 5, 6), (9, 6, 3), (10, 6, 3), (6, 6, 20)])
+def test_vectors_larger_than_shared_memory(kron, oracle_mod, n, d, nb):
+    """The top of the reference's sweep envelope (tests/kronmult_fullbench_gpu.cpp:70-74): n^d up to 10^6."""
+    for alias, kw in (("runs", dict(items_per_output=3)), ("ref", dict(nb_distinct=2))):
+        hp = batch.make_problem(d, n, nb, torch.float64, "cpu", seed=n + d, alias=alias, lda=n + 1, **kw).to_host()
+        _check(kron, oracle_mod, hp)
 
 
 SWEEP = [(n, d) for n in range(2, 11) for d in range(1, 7) if n ** d <= 20000]

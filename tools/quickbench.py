@@ -23,6 +23,11 @@ CONFIGS = {
     "c4b": (4, 8, 1 << 19, torch.float64, 32),
     "c5_f64": (5, 4, 1 << 23, torch.float64, 32),
     "c5_f32": (5, 4, 1 << 23, torch.float32, 32),
+    # the reference's named cases (tests/kronmult_bench_gpu.cpp:68-72): stride 67, 5 distinct outputs
+    "ref_medium": (3, 6, 384, torch.float64, "ref"),
+    "ref_large": (6, 8, 896, torch.float64, "ref"),
+    "ref_realistic": (6, 8, 3903, torch.float64, "ref"),
+    "ref_realistic_f32": (6, 8, 3903, torch.float32, "ref"),
 }
 
 
@@ -50,8 +55,11 @@ def main():
     for name in args.configs.split(","):
         d, n, nb, dt, r = CONFIGS[name]
         nb = max(1, int(nb * args.scale))
-        alias = args.alias or ("runs" if r > 1 else "distinct")
-        p = batch.make_problem(d, n, nb, dt, "cuda", seed=993, alias=alias, items_per_output=r)
+        if r == "ref":
+            p = batch.make_problem(d, n, nb, dt, "cuda", seed=993, alias="ref", nb_distinct=5, matrices="reftest")
+        else:
+            alias = args.alias or ("runs" if r > 1 else "distinct")
+            p = batch.make_problem(d, n, nb, dt, "cuda", seed=993, alias=alias, items_per_output=r)
         A, i, o, w = p.pointer_arrays()
         api.force_path(args.path)
         torch.cuda.synchronize()  # the problem was built on the default stream
