@@ -238,26 +238,51 @@ static cudaError_t launch_dmma84(int sms, const double *const *A, int lda, doubl
 // The reference moves 2 x N x 8 bytes through global memory per FACTOR (kronmult.cu:112-121); this moves
 // 3 x N x 8 bytes per ITEM.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(Dmma84::THREADS, 3)
+// Pass A is a pure streaming pass (read 32 KiB, 512 DMMAs, write 32 KiB per tile), so it is built as a
+// 3-stage TMA ring: one elected thread fetches the tile two units ahead with a single cp.async.bulk; phase 1
+// reads its 512-byte slices from the ring slot and writes them back swizzled IN PLACE (a slice is read and
+// written by one warp instruction pair), phase 2 works in place too, and the write-back streams the slot
+// linearly to global memory.  Factor fragments are fetched one unit ahead, their pointers two.
+__global__ void __launch_bounds__(Dmma84::THREADS, 2)
 kron_dmma8_tile4_kernel(const double *const *__restrict__ A, double *const *__restrict__ in, const int lda,
                         const int d, const int tiles_per_item, const long long total_units)
 {
     using C = Dmma84;
-    constexpr int N = C::N, T1 = C::T1, P2 = C::P2;
+    constexpr int N = C::N, T1 = C::T1, P2 = C::P2, NST = 3;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *E = reinterpret_cast<double *>(smem_raw); // [2][4096]
+    double *R     = reinterpret_cast<double *>(smem_raw);            // [3][4096] ring of tiles
+    uint64_t *bar = reinterpret_cast<uint64_t *>(R + NST * N);      // [3] "tile landed"
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
     const int g = lane >> 2, q = lane & 3;
     const int lane_off0 = g + (2 * q) * lda;
 
-    int it = 0;
-    for (long long u = blockIdx.x; u < total_units; u += gridDim.x, ++it)
+    if (t == 0)
     {
+        for (int i = 0; i < NST; ++i) mbar_init(bar + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto unit_of  = [&](int it) { return (long long)blockIdx.x + (long long)it * gridDim.x; };
+    auto tile_ptr = [&](long long u) -> double * {
         const long long k = u / tiles_per_item;
-        const int tile    = (int)(u - k * tiles_per_item);
-        double *base      = in[k] + (long long)tile * N;
-        double *Ec        = E + (it & 1) * N;
-        double a[8];
+        return in[k] + (u - k * tiles_per_item) * N;
+    };
+    // fetch unit `it` into ring slot it % 3 (thread 0 only).  Unaligned tiles are loaded by everybody in fill().
+    auto issue = [&](int it) {
+        const long long u = unit_of(it);
+        if (u >= total_units) return;
+        double *src = tile_ptr(u);
+        if (aligned16(src))
+        {
+            fence_proxy_async();
+            mbar_arrive_expect_tx(bar + it % NST, N * 8);
+            tma_load_1d(R + (it % NST) * N, src, N * 8, bar + it % NST);
+        }
+        else mbar_arrive(bar + it % NST);
+    };
+    auto load_frags = [&](long long u, double (&a)[8]) {
+        const long long k = u / tiles_per_item;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
         {
@@ -265,30 +290,52 @@ kron_dmma8_tile4_kernel(const double *const *__restrict__ A, double *const *__re
             a[2 * j]     = __ldg(p0 + lane_off0);
             a[2 * j + 1] = __ldg(p0 + lane_off0 + lda);
         }
-        const bool vec = aligned16(base);
-        // phase 1: the two fastest indices
+    };
+
+    if (t == 0) { issue(0); issue(1); }
+    double a_nxt[8];
+    if (unit_of(0) < total_units) load_frags(unit_of(0), a_nxt);
+    unsigned parity = 0; // bit i = phase parity of ring slot i
+
+    for (int it = 0; unit_of(it) < total_units; ++it)
+    {
+        const long long u = unit_of(it);
+        const int slot    = it % NST;
+        double *Ec        = R + slot * N;
+        double *base      = tile_ptr(u);
+        const bool vec    = aligned16(base);
+        double a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = a_nxt[i];
+        if (unit_of(it + 1) < total_units) load_frags(unit_of(it + 1), a_nxt);
+
+        mbar_wait(bar + slot, (parity >> slot) & 1u);
+        parity ^= 1u << slot;
+        // phase 1: the two fastest indices, slice by slice, in place
 #pragma unroll
         for (int tt = 0; tt < T1; ++tt)
         {
-            const int h       = w * T1 + tt;
-            const double *src = base + h * 64 + g * 8 + 2 * q;
+            const int h = w * T1 + tt;
             double x0, x1;
             if (vec)
             {
-                const double2 v = *reinterpret_cast<const double2 *>(src);
+                const double2 v = *reinterpret_cast<const double2 *>(Ec + h * 64 + g * 8 + 2 * q);
                 x0 = v.x; x1 = v.y;
             }
-            else { x0 = src[0]; x1 = src[1]; }
+            else { x0 = base[h * 64 + g * 8 + 2 * q]; x1 = base[h * 64 + g * 8 + 2 * q + 1]; }
             double y0, y1, z0, z1;
             dmma884(y0, y1, a[6], x0, 0.0, 0.0);
             dmma884(y0, y1, a[7], x1, y0, y1);
             dmma884(z0, z1, a[4], y0, 0.0, 0.0);
             dmma884(z0, z1, a[5], y1, z0, z1);
+            __syncwarp(); // every lane has read its chunk of the slice before the slice is rewritten
             const int chunk16 = (4 * g + q) ^ dmma_sigma(h);
             *reinterpret_cast<double2 *>(Ec + h * 64 + chunk16 * 2) = make_double2(z0, z1);
         }
         __syncthreads();
-        // phase 2: the next two indices; results go back to the slots this warp alone read
+        // everyone has left the previous unit (its write-back read slot (it+2)%3): refill that slot
+        if (t == 0) issue(it + 2);
+        // phase 2: the next two indices, slice pairs, in place
 #pragma unroll
         for (int jj = 0; jj < P2; ++jj)
         {
@@ -321,7 +368,6 @@ kron_dmma8_tile4_kernel(const double *const *__restrict__ A, double *const *__re
             if (vec) *reinterpret_cast<double2 *>(base + 2 * c) = v;
             else { base[2 * c] = v.x; base[2 * c + 1] = v.y; }
         }
-        // the other exchange buffer is used next; its readers finished before the second barrier above
     }
 }
 
@@ -433,6 +479,7 @@ kron_dmma8_rows2_kernel(const double *const *__restrict__ A, double *const *__re
 }
 
 // pass A for n = 8, d >= 5: the four fastest factors, in place
+static constexpr int TILE4_SMEM = 3 * Dmma84::N * 8 + 64;
 static cudaError_t launch_dmma8_tile4(int sms, int d, long long N, const double *const *A, int lda, double *const *in,
                                       int nb, cudaStream_t st, std::atomic<long long> &launches)
 {
@@ -440,15 +487,15 @@ static cudaError_t launch_dmma8_tile4(int sms, int d, long long N, const double 
     static bool attr_done = false;
     if (!attr_done)
     {
-        cudaError_t e = cudaFuncSetAttribute(kron_dmma8_tile4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(kron_dmma8_tile4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE4_SMEM);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
     const int tpi            = (int)(N / C::N);
     const long long units    = (long long)nb * tpi;
-    const long long max_grid = (long long)sms * 3;
+    const long long max_grid = (long long)sms * 2;
     const int grid           = (int)(units < max_grid ? units : max_grid);
-    kron_dmma8_tile4_kernel<<<grid, C::THREADS, C::SMEM, st>>>(A, in, lda, d, tpi, units);
+    kron_dmma8_tile4_kernel<<<grid, C::THREADS, TILE4_SMEM, st>>>(A, in, lda, d, tpi, units);
     launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
