@@ -1,0 +1,414 @@
+// kernel_wspec5.cuh -- warp-specialised two-phase kernel for n = 4, d = 5 ("wspec5" path, BASELINE config 5).
+//
+// Replaces cuda_kronmult_batchelement / cuda_kronmult / multiply_transpose
+// (kronmult_gpu/kronmult.cu:139-167, :95-130, :54-78).
+//
+// Same split of the work as kernel_wspec.cuh (P1 warps: the two slow factors, column-wise; P2 warps: the three
+// fast factors, row-wise, with run accumulators in registers), re-cut so that more warps are resident:
+// ncu on the 4-items-per-step version showed two 255-register warps per scheduler issuing 37 % of the cycles,
+// the consumer waiting on a single exchange buffer.  Here
+//   * a step is TWO items (slot q = P1 warp q = P2 warp q), so the exchange buffer E (32 rows) can be double
+//     buffered and three (fp64) or more (fp32) CTAs fit one SM;
+//   * a row of E is shared by two P2 threads: lane l and lane l+16 both read the row's 16-value slices, but
+//     each computes only two of the four fastest output indices (i4' in {2hf, 2hf+1}), so no arithmetic is
+//     duplicated and a thread carries 32 accumulators instead of 64;
+//   * an item's flush is the business of ONE warp (__syncwarp, no named barrier);
+//   * a CTA is IPS independent pipelines (P1 warp q -> P2 warp q) that share nothing: every mbarrier has one
+//     producer warp and one consumer warp, there is no CTA-wide or named barrier in the loop;
+//   * whole items are pulled into L2 two steps ahead with one cp.async.bulk.prefetch.L2 each, the TMA copy into
+//     the 2-stage ring follows one step ahead; the five factors of an item are staged two steps ahead (5-deep
+//     ring) by TMA as well -- one 640-byte copy when they are contiguous (dense batches), one per factor or per
+//     column otherwise, element-wise cp.async only when alignment rules TMA out;
+// Per output element the products are accumulated k ascending from 0 like multiply_transpose
+// (kronmult.cu:66-70); factors are applied slowest index first.
+#pragma once
+#include "common.cuh"
+#include "kernel_regtile.cuh"
+#include "kernel_wspec.cuh"
+#include <atomic>
+
+namespace kron
+{
+
+template<typename T>
+struct Wspec5
+{
+    static constexpr int D       = 5;
+    static constexpr int N       = 1024;
+    static constexpr int IPS     = 2;                              // item streams (warp pairs) per CTA
+    static constexpr int PITCH   = 64 + 16 / (int)sizeof(T);       // padded row of E, in elements
+    static constexpr int NE      = 2;                              // exchange buffers per stream
+    static constexpr int NST     = 2;                              // TMA ring stages per stream
+    static constexpr int NMB     = 5;                              // factor ring depth (see the P1 loop)
+    static constexpr int MINB    = (sizeof(T) == 4) ? 4 : 3;       // resident CTAs per SM aimed at
+    static constexpr int MSTR    = D * 16;                         // per-item factor block: 5 column-major 4x4
+    static constexpr int THREADS = 64 * IPS;
+    static constexpr int IN_EL   = IPS * NST * N;
+    static constexpr int E_EL    = IPS * NE * 16 * PITCH;
+    static constexpr int MS_EL   = IPS * NMB * MSTR;
+    static constexpr int NBAR    = IPS * (NST + NMB + 2 * NE);
+    static constexpr int SMEM    = (IN_EL + E_EL + MS_EL) * (int)sizeof(T) + 8 * NBAR + 16;
+};
+
+__device__ __forceinline__ void l2_prefetch_bulk(const void *gsrc, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+
+// Two-wide values: a thread works on pairs of independent outputs that share the factor element.  For float the
+// pair operations are the packed FFMA2 / FMUL2 of sm_100 (one issue slot for two FMAs; the scalar operand is
+// broadcast by the instruction itself), for double they are two DFMA / DMUL.
+template<typename T> struct V2;
+template<> struct V2<float>  { using type = float2; };
+template<> struct V2<double> { using type = double2; };
+__device__ __forceinline__ float2 pmul(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+__device__ __forceinline__ float2 pfma(float2 a, float s, float2 c) { return __ffma2_rn(a, make_float2(s, s), c); }
+__device__ __forceinline__ double2 pmul(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
+__device__ __forceinline__ double2 pfma(double2 a, double s, double2 c)
+{
+    return make_double2(fma(a.x, s, c.x), fma(a.y, s, c.y));
+}
+
+// x is a 4x4 tile of pairs indexed hi*4+lo; m is a COLUMN-major factor (m[k*4+i] = M(i,k)).
+// STRIDE = 1: apply M along lo; STRIDE = 4: along hi.  Products are accumulated k ascending.
+template<typename T, int STRIDE>
+__device__ __forceinline__ void tile16_apply_cm2(typename V2<T>::type (&x)[16], const T (&m)[16])
+{
+    using P = typename V2<T>::type;
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+    {
+        const int base = (STRIDE == 1) ? f * 4 : f;
+        const P a0 = x[base], a1 = x[base + STRIDE], a2 = x[base + 2 * STRIDE], a3 = x[base + 3 * STRIDE];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            P dot = pmul(a0, m[i]);
+            dot   = pfma(a1, m[4 + i], dot);
+            dot   = pfma(a2, m[8 + i], dot);
+            dot   = pfma(a3, m[12 + i], dot);
+            x[base + i * STRIDE] = dot;
+        }
+    }
+}
+
+template<typename T>
+__global__ void __launch_bounds__(Wspec5<T>::THREADS, Wspec5<T>::MINB)
+kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T *const *__restrict__ out,
+                   const int lda, const int nb, const long long items_per_cta, const int sms)
+{
+    using C = Wspec5<T>;
+    constexpr int D = 5, N = C::N, IPS = C::IPS, PITCH = C::PITCH, NMB = C::NMB, NE = C::NE, NST = C::NST;
+    constexpr int MSTR = C::MSTR;
+    constexpr unsigned ITEM_BYTES = N * sizeof(T), FAC_BYTES = 16 * sizeof(T), COL_BYTES = 4 * sizeof(T);
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int t    = threadIdx.x;
+    const int lane = t & 31;
+    const int w    = t >> 5;
+    // Warp w runs on SM sub-partition w % 4.  Co-resident CTAs swap the roles of their warp pairs so that every
+    // sub-partition hosts P1 and P2 warps.
+    const bool swap_roles = ((blockIdx.x / sms) & 1) != 0;
+    const int q           = w % IPS;                      // item stream of this warp
+    const bool is_p1      = ((w / IPS) == 0) != swap_roles;
+
+    // shared memory of stream q: nothing is shared between streams
+    T *IN          = reinterpret_cast<T *>(smem_raw) + q * (NST * N);                      // [NST][N]   TMA ring
+    T *E           = reinterpret_cast<T *>(smem_raw) + C::IN_EL + q * (NE * 16 * PITCH);   // [NE][16][PITCH]
+    T *MS          = reinterpret_cast<T *>(smem_raw) + C::IN_EL + C::E_EL + q * (NMB * MSTR); // [NMB][MSTR]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (C::IN_EL + C::E_EL + C::MS_EL) * sizeof(T))
+                     + q * (NST + NMB + 2 * NE);
+    uint64_t *full_in = bars, *m_full = bars + NST, *e_full = bars + NST + NMB, *e_empty = bars + NST + NMB + NE;
+
+    // this CTA's items, split into IPS consecutive streams: stream q takes [kq0, kq0 + cnt)
+    const long long K0 = (long long)blockIdx.x * items_per_cta;
+    long long K1       = K0 + items_per_cta;
+    if (K1 > nb) K1 = nb;
+    if (K1 <= K0) return;
+    const int tot = (int)(K1 - K0);
+    const int len = (tot + IPS - 1) / IPS;
+    int cnt       = tot - q * len;
+    cnt           = cnt < 0 ? 0 : (cnt > len ? len : cnt);
+    const long long kq0 = K0 + (long long)q * len;
+
+    if (t < IPS)
+    {
+        uint64_t *b = reinterpret_cast<uint64_t *>(smem_raw + (C::IN_EL + C::E_EL + C::MS_EL) * sizeof(T))
+                      + t * (NST + NMB + 2 * NE);
+        for (int i = 0; i < NST + NMB + 2 * NE; ++i) mbar_init(b + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (cnt == 0) return;
+
+    if (is_p1)
+    {
+        // =================================================================== P1: two slow factors, column-wise
+        // lane j < 5 holds the pointer of factor j; every lane holds the vector pointer
+        auto fac_ptr = [&](int s) -> const T * { return (s < cnt && lane < D) ? A[(kq0 + s) * D + lane] : nullptr; };
+        auto in_ptr  = [&](int s) -> const T * { return (s < cnt) ? in[kq0 + s] : nullptr; };
+        // vector of step s -> ring stage s % NST: one TMA bulk copy when it is 16-byte aligned (lane 0), else
+        // element-wise cp.async by the whole warp.  Returns true for the element-wise route.
+        auto stage_data = [&](int s, const T *ip) -> bool {
+            if (s >= cnt) return false;
+            T *dst         = IN + (s % NST) * N;
+            const bool tma = aligned16(ip);
+            if (!tma)
+            {
+#pragma unroll 8
+                for (int h = 0; h < N / 32; ++h) cp_async_elem<T>(dst + h * 32 + lane, ip + h * 32 + lane);
+            }
+            if (lane == 0)
+            {
+                if (tma)
+                {
+                    fence_proxy_async(); // this warp's generic-proxy reads of the stage come first
+                    mbar_arrive_expect_tx(full_in + (s % NST), ITEM_BYTES);
+                    tma_load_1d(dst, ip, ITEM_BYTES, full_in + (s % NST));
+                }
+                else mbar_arrive(full_in + (s % NST));
+            }
+            return !tma;
+        };
+        // factors of step s -> ring slot s % NMB as five compact column-major 4x4 blocks.  By TMA when the layout
+        // allows (one copy per item, per factor or per column), else element-wise.  Returns true for element-wise.
+        auto stage_facs = [&](int s, const T *ap) -> bool {
+            if (s >= cnt) return false;
+            T *dst         = MS + (s % NMB) * MSTR;
+            uint64_t *bar  = m_full + (s % NMB);
+            const T *ap0   = reinterpret_cast<const T *>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ap), 0));
+            const bool a16 = __all_sync(0xffffffffu, lane >= D || aligned16(ap));
+            bool elem      = false;
+            if (a16 && lda == 4)
+            {
+                const bool contig = __all_sync(0xffffffffu, lane >= D || ap == ap0 + lane * 16);
+                if (lane == 0)
+                {
+                    fence_proxy_async();
+                    mbar_arrive_expect_tx(bar, D * FAC_BYTES);
+                    if (contig) tma_load_1d(dst, ap0, D * FAC_BYTES, bar);
+                }
+                __syncwarp();
+                if (!contig && lane < D) tma_load_1d(dst + lane * 16, ap, FAC_BYTES, bar);
+            }
+            else if (a16 && (lda * (int)sizeof(T)) % 16 == 0)
+            {
+                if (lane == 0)
+                {
+                    fence_proxy_async();
+                    mbar_arrive_expect_tx(bar, D * FAC_BYTES);
+                }
+                __syncwarp();
+                const T *apj = reinterpret_cast<const T *>(
+                    __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ap), (lane >> 2) % D));
+                if (lane < 4 * D) tma_load_1d(dst + lane * 4, apj + (long long)(lane & 3) * lda, COL_BYTES, bar);
+            }
+            else
+            {
+                elem = true;
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                {
+                    const int e  = lane + 32 * i; // element e = factor e/16, column (e%16)/4, row e%4
+                    const T *apj = reinterpret_cast<const T *>(
+                        __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ap), (e >> 4) % D));
+                    if (e < D * 16) cp_async_elem<T>(dst + e, apj + (e & 3) + (long long)((e >> 2) & 3) * lda);
+                }
+                if (lane == 0) mbar_arrive(bar);
+            }
+            return elem;
+        };
+        auto l2_pull = [&](const T *ip) {
+            if (lane == 0 && ip && aligned16(ip)) l2_prefetch_bulk(ip, ITEM_BYTES);
+        };
+
+        // prologue: vector of step 0, L2 pull of step 1, factors of steps 0 and 1
+        const T *ip_b = in_ptr(1), *ip_c = in_ptr(2);   // inside the loop: vectors of steps s+1 and s+2
+        const T *ap_c = fac_ptr(2);                     //                  factor pointers of step s+2
+        bool el_0 = stage_data(0, in_ptr(0));           // element-wise copies in flight for step s ...
+        el_0 |= stage_facs(0, fac_ptr(0));
+        bool el_1 = stage_facs(1, fac_ptr(1));          // ... and for step s+1
+        l2_pull(ip_b);
+        cp_async_commit();
+
+        for (int s = 0; s < cnt; ++s)
+        {
+            const int st = s % NST;
+            const T *ip_d = in_ptr(s + 3);       // pointer pipeline: fetched now, used next step
+            const T *ap_d = fac_ptr(s + 3);
+
+            // the stage and the factor slot written below were last read in step s-1 / s-3 by this warp and in
+            // step s-3 by its P2 warp, which ended before this warp passed e_empty in step s-1
+            bool el_2 = stage_facs(s + 2, ap_c);
+            el_1 |= stage_data(s + 1, ip_b);
+            cp_async_commit();
+            l2_pull(ip_c);                       // step s+2; its pointer was fetched a step ago
+            if (el_0)
+            {
+                // element-wise route (vectors or factors that TMA cannot take): wait for the copies of step s,
+                // which were committed at least one group ago
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+                __syncwarp();
+            }
+            mbar_wait(full_in + st, (unsigned)(s / NST) & 1u);
+            mbar_wait(m_full + (s % NMB), (unsigned)(s / NMB) & 1u);
+
+            using P = typename V2<T>::type;
+            P x[16]; // x[h] = my two adjacent columns of row h = (i0, i1)
+            {
+                const T *src = IN + st * N + 2 * lane;
+#pragma unroll
+                for (int h = 0; h < 16; ++h) x[h] = *reinterpret_cast<const P *>(src + h * 64);
+                const T *Ms = MS + (s % NMB) * MSTR;
+                T m1[16], m0[16];
+                lds16<T>(Ms + 1 * 16, m1);
+                lds16<T>(Ms + 0 * 16, m0);
+                tile16_apply_cm2<T, 1>(x, m1);
+                tile16_apply_cm2<T, 4>(x, m0);
+            }
+            const int eb = s % NE;
+            T *Eb        = E + eb * 16 * PITCH;
+            mbar_wait(e_empty + eb, (((unsigned)(s / NE)) & 1u) ^ 1u); // first use passes on a fresh barrier
+#pragma unroll
+            for (int h = 0; h < 16; ++h) *reinterpret_cast<P *>(Eb + h * PITCH + 2 * lane) = x[h];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(e_full + eb);
+
+            ip_b = ip_c; ip_c = ip_d; ap_c = ap_d;
+            el_0 = el_1; el_1 = el_2;
+        }
+    }
+    else
+    {
+        // =================================================================== P2: three fast factors + run sums, row-wise
+        using P = typename V2<T>::type;
+        const int row = lane & 15, hf = lane >> 4;
+        P acc[16]; // acc[i2' * 4 + i3'] = the pair i4' = 2 hf, 2 hf + 1
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i].x = acc[i].y = T(0);
+        T *o_cur  = out[kq0];
+        T *o_next = (cnt > 1) ? out[kq0 + 1] : nullptr; // output pointers are fetched two steps ahead
+
+        for (int s = 0; s < cnt; ++s)
+        {
+            T *o_next2   = (s + 2 < cnt) ? out[kq0 + s + 2] : nullptr;
+            const int eb = s % NE;
+            T *Eb        = E + eb * 16 * PITCH;
+            T *erow      = Eb + row * PITCH;
+            const T *Mq  = MS + (s % NMB) * MSTR;
+            mbar_wait(e_full + eb, (unsigned)(s / NE) & 1u);
+            mbar_wait(m_full + (s % NMB), (unsigned)(s / NMB) & 1u); // complete long ago: makes the TMA writes visible here
+            {
+                // f4[k] = (F4(2hf, k), F4(2hf+1, k)): my two rows of the fastest factor; f3: the second fastest
+                P f4[4];
+                T f3[16];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) f4[k] = *reinterpret_cast<const P *>(Mq + 4 * 16 + k * 4 + 2 * hf);
+                lds16<T>(Mq + 3 * 16, f3);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                {
+                    T x[16], f2[4];
+                    lds16<T>(erow + j * 16, x);
+                    // fastest index: y[i3] = sum_k x[i3][k] F4(2hf + {0,1}, k)
+                    P y[4];
+#pragma unroll
+                    for (int i3 = 0; i3 < 4; ++i3) y[i3] = pmul(f4[0], x[i3 * 4]);
+#pragma unroll
+                    for (int k = 1; k < 4; ++k)
+#pragma unroll
+                        for (int i3 = 0; i3 < 4; ++i3) y[i3] = pfma(f4[k], x[i3 * 4 + k], y[i3]);
+                    // second fastest: z[i3'] = sum_i3 F3(i3', i3) y[i3]
+                    P z[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) z[i] = pmul(y[0], f3[i]);
+#pragma unroll
+                    for (int k = 1; k < 4; ++k)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) z[i] = pfma(y[k], f3[k * 4 + i], z[i]);
+                    // third: acc[i2'][i3'] += F2(i2', j) z[i3']   (column j of F2 is contiguous)
+                    if constexpr (sizeof(T) == 8)
+                    {
+                        const double2 v0 = reinterpret_cast<const double2 *>(Mq + 2 * 16 + j * 4)[0];
+                        const double2 v1 = reinterpret_cast<const double2 *>(Mq + 2 * 16 + j * 4)[1];
+                        f2[0] = v0.x; f2[1] = v0.y; f2[2] = v1.x; f2[3] = v1.y;
+                    }
+                    else
+                    {
+                        const float4 v = *reinterpret_cast<const float4 *>(Mq + 2 * 16 + j * 4);
+                        f2[0] = v.x; f2[1] = v.y; f2[2] = v.z; f2[3] = v.w;
+                    }
+#pragma unroll
+                    for (int i2 = 0; i2 < 4; ++i2)
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) acc[i2 * 4 + m] = pfma(z[m], f2[i2], acc[i2 * 4 + m]);
+                }
+            }
+            // ---- flush when the run of equal output pointers ends here: the accumulators go back into the rows
+            // of E this warp owns, then the warp reads E column-wise so that the REDs of its lanes are contiguous
+            // (sector-complete).  One item = one warp, so __syncwarp orders everything.
+            if (o_next != o_cur)
+            {
+                __syncwarp(); // both threads of a row are done reading it
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                {
+                    *reinterpret_cast<P *>(erow + i * 4 + 2 * hf) = acc[i];
+                    acc[i].x = acc[i].y = T(0);
+                }
+                __syncwarp();
+#pragma unroll 4
+                for (int h = 0; h < 16; ++h)
+                {
+                    red_add(o_cur + h * 64 + lane, Eb[h * PITCH + lane]);
+                    red_add(o_cur + h * 64 + 32 + lane, Eb[h * PITCH + 32 + lane]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(e_empty + eb); // every read of E and of this step's factors is done
+            o_cur  = o_next;
+            o_next = o_next2;
+        }
+    }
+}
+
+template<typename T>
+static cudaError_t launch_wspec5(int sms, const T *const *A, int lda, T *const *in, T *const *out, int nb,
+                                 cudaStream_t st, std::atomic<long long> &launches)
+{
+    using C  = Wspec5<T>;
+    auto kfn = kron_wspec5_kernel<T>;
+    static int ctas_per_sm = 0; // benign race: idempotent
+    if (ctas_per_sm == 0)
+    {
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) return e;
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, C::THREADS, C::SMEM);
+        if (e != cudaSuccess) return e;
+        ctas_per_sm = occ > 0 ? occ : 1;
+    }
+    long long grid = (long long)sms * ctas_per_sm;
+    long long ipc  = ((long long)nb + grid - 1) / grid; // items per CTA
+    // CTA and stream boundaries on multiples of 32 items when there is enough work, so that ASGarD-style
+    // runs of equal output pointers do not straddle streams
+    const long long align = 32LL * C::IPS;
+    if (ipc > 2 * align) ipc = (ipc + align - 1) / align * align;
+    grid = ((long long)nb + ipc - 1) / ipc;
+    kfn<<<(int)grid, C::THREADS, C::SMEM, st>>>(A, in, out, lda, nb, ipc, sms);
+    launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+// cudaErrorNotSupported when (n, d) is outside the family
+template<typename T>
+static cudaError_t run_wspec5(int sms, int d, int n, const T *const *A, int lda, T *const *in, T *const *out, int nb,
+                              cudaStream_t st, std::atomic<long long> &launches, const char *&last_path)
+{
+    if (n != 4 || d != 5) return cudaErrorNotSupported;
+    cudaError_t e = launch_wspec5<T>(sms, A, lda, in, out, nb, st, launches);
+    last_path = "wspec5";
+    return e;
+}
+
+} // namespace kron

@@ -15,6 +15,7 @@
 #include "kernel_regtile.cuh"
 #include "kernel_dmma.cuh"
 #include "kernel_wspec.cuh"
+#include "kernel_wspec5.cuh"
 
 #include <atomic>
 #include <mutex>
@@ -272,6 +273,11 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
         e = run_wspec<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
         return e == cudaErrorNotSupported ? cudaErrorInvalidValue : e;
     }
+    if (force == PATH_WSPEC5)
+    {
+        e = run_wspec5<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
+        return e == cudaErrorNotSupported ? cudaErrorInvalidValue : e;
+    }
     if (force == PATH_DMMA)
     {
         int remaining = 0;
@@ -289,6 +295,8 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
         if (e == cudaSuccess && remaining > 0) e = run_generic<T>(di, d, n, A, lda, in, out, nb, st, d - remaining);
         if (e != cudaErrorNotSupported) return e;
     }
+    e = run_wspec5<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
+    if (e != cudaErrorNotSupported) return e;
     e = run_wspec<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
     if (e != cudaErrorNotSupported) return e;
     e = run_regtile<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
@@ -356,7 +364,7 @@ int kronmult_b200_set_tuning(int knob, int value)
 }
 int kronmult_b200_force_path(int path)
 {
-    if (path < kron::PATH_AUTO || path > kron::PATH_WSPEC) return (int)cudaErrorInvalidValue;
+    if (path < kron::PATH_AUTO || path > kron::PATH_LAST) return (int)cudaErrorInvalidValue;
     kron::g_force.store(path);
     return 0;
 }

@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--fp64-tflops", type=float, default=37.0)
     ap.add_argument("--fp32-tflops", type=float, default=75.0)
     ap.add_argument("--alias", default=None)
+    ap.add_argument("--telemetry", action="store_true", help="NVML SM clock / power after every rep")
     ap.add_argument("--tune", default=None, help="knob=value[,knob=value] for kronmult_b200_set_tuning")
     args = ap.parse_args()
     hbm = 6552.3
@@ -47,6 +48,11 @@ def main():
     if os.path.exists(mp):
         hbm = json.load(open(mp)).get("hbm_gbs", hbm)
     torch.cuda.set_device(0)
+    nv = None
+    if args.telemetry:
+        import pynvml
+        pynvml.nvmlInit()
+        nv = pynvml.nvmlDeviceGetHandleByIndex(0)
     stream = torch.cuda.Stream()
     if args.tune:
         for kv in args.tune.split(","):
@@ -63,7 +69,7 @@ def main():
         A, i, o, w = p.pointer_arrays()
         api.force_path(args.path)
         torch.cuda.synchronize()  # the problem was built on the default stream
-        times = []
+        times, tele = [], []
         with torch.cuda.stream(stream):
             for rep in range(args.reps + 2):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -73,6 +79,9 @@ def main():
                 e1.synchronize()
                 if rep >= 2:
                     times.append(e0.elapsed_time(e1))
+                if nv is not None:
+                    tele.append((pynvml.nvmlDeviceGetClockInfo(nv, pynvml.NVML_CLOCK_SM),
+                                 round(pynvml.nvmlDeviceGetPowerUsage(nv) / 1000)))
         api.force_path("auto")
         t = min(times) * 1e-3
         fl, by = p.flops(), p.algorithmic_bytes()
@@ -81,7 +90,8 @@ def main():
         print(json.dumps({"config": name, "path": api.last_path(), "nb": nb, "ms": round(t * 1e3, 4),
                           "ms_all": [round(x, 4) for x in times], "gflops": round(fl / t * 1e-9, 1),
                           "alg_gbs": round(by / t * 1e-9, 1), "roofline_ms": round(roof * 1e3, 4),
-                          "frac": round(roof / t, 4), "bound": "hbm" if by / (hbm * 1e9) >= fl / peak else "fp"}),
+                          "frac": round(roof / t, 4), "bound": "hbm" if by / (hbm * 1e9) >= fl / peak else "fp",
+                          **({"sm_mhz_power_w": tele} if tele else {})}),
               flush=True)
         del p, A, i, o, w
         torch.cuda.empty_cache()
