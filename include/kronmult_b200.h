@@ -61,6 +61,27 @@ int kronmult_batched_host_f32(int d, int n, const float *const *A, int lda, floa
 int kronmult_partition_by_output(const void *const *out, int nb, int n_ranks, long long split_threshold,
                                  int *owner, unsigned char *needs_reduce);
 
+/* Batch / aliasing planner (no reference counterpart; BASELINE.json north_star).  Every kernel sums runs of
+ * consecutive items that share an output pointer on chip; a plan sorts the batch by output pointer on the
+ * device (stable, so equal pointers keep their batch order) and keeps sorted copies of the three pointer
+ * arrays when that at least halves the number of runs.  The pointer arrays given to kronmult_plan_create_*
+ * (DEVICE arrays, same meaning as above) must stay alive and unchanged while the plan is used; the vectors
+ * and factors they point to may change freely between executions (ASGarD: same pointers every time step).
+ * create blocks until the plan is built; execute is stream-ordered like the _async entry points.  The blocking
+ * entry points above build and cache such plans on their own (knob 1 of kronmult_b200_set_tuning, default on). */
+typedef struct kronmult_plan kronmult_plan;
+int kronmult_plan_create_f64(int d, int n, const double *const *A, int lda, double **in, double **out, int nb,
+                             void *stream, kronmult_plan **plan);
+int kronmult_plan_create_f32(int d, int n, const float *const *A, int lda, float **in, float **out, int nb,
+                             void *stream, kronmult_plan **plan);
+int kronmult_plan_execute(const kronmult_plan *plan, void *stream);
+/* runs of equal consecutive output pointers before / after sorting; permuted = 1 if the sorted order is used */
+int kronmult_plan_stats(const kronmult_plan *plan, long long *runs_before, long long *runs_after, int *permuted);
+int kronmult_plan_destroy(kronmult_plan *plan);
+/* implicit plans of the blocking entry points: cache hits / plans built so far in this process */
+long long kronmult_b200_plan_cache_hits(void);
+long long kronmult_b200_plan_cache_builds(void);
+
 /* Introspection used by the test-suite and bench.py. */
 const char *kronmult_b200_version(void);
 /* number of kernels this library has launched in this process so far */
@@ -70,7 +91,8 @@ const char *kronmult_b200_last_path(void);
 /* 0 = automatic dispatch; otherwise force a kernel family (see kronmult993_b200/csrc/dispatch.h).
  * Unsupported combinations make the next call return cudaErrorInvalidValue.  For tests. */
 int kronmult_b200_force_path(int path);
-/* development knobs (knob 0: regtile operand staging, 0 = TMA into shared memory, 1 = L1 prefetch). */
+/* knobs.  0: regtile operand staging (0 = TMA into shared memory, 1 = L1 prefetch; development).
+ *         1: implicit planning in the blocking entry points (1 = on, default; 0 = off). */
 int kronmult_b200_set_tuning(int knob, int value);
 
 #ifdef __cplusplus

@@ -36,6 +36,13 @@ C_SYMBOLS = (
     "kronmult_batched_host_f64",
     "kronmult_batched_host_f32",
     "kronmult_partition_by_output",
+    "kronmult_plan_create_f64",
+    "kronmult_plan_create_f32",
+    "kronmult_plan_execute",
+    "kronmult_plan_stats",
+    "kronmult_plan_destroy",
+    "kronmult_b200_plan_cache_hits",
+    "kronmult_b200_plan_cache_builds",
     "kronmult_b200_version",
     "kronmult_b200_launch_count",
     "kronmult_b200_last_path",
@@ -86,6 +93,15 @@ def load_library() -> ctypes.CDLL:
         f.restype, f.argtypes = c_int, [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp]
         f = getattr(lib, f"kronmult_batched_host_{sfx}")
         f.restype, f.argtypes = c_int, [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int]
+        f = getattr(lib, f"kronmult_plan_create_{sfx}")
+        f.restype, f.argtypes = c_int, [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_vp, ctypes.POINTER(c_vp)]
+    lib.kronmult_plan_execute.restype, lib.kronmult_plan_execute.argtypes = c_int, [c_vp, c_vp]
+    lib.kronmult_plan_stats.restype = c_int
+    lib.kronmult_plan_stats.argtypes = [c_vp, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong),
+                                        ctypes.POINTER(c_int)]
+    lib.kronmult_plan_destroy.restype, lib.kronmult_plan_destroy.argtypes = c_int, [c_vp]
+    lib.kronmult_b200_plan_cache_hits.restype = ctypes.c_longlong
+    lib.kronmult_b200_plan_cache_builds.restype = ctypes.c_longlong
     lib.kronmult_pow_int.restype, lib.kronmult_pow_int.argtypes = c_int, [c_int, c_int]
     lib.kronmult_partition_by_output.restype = c_int
     lib.kronmult_partition_by_output.argtypes = [c_vp, c_int, c_int, ctypes.c_longlong, c_vp, c_vp]
@@ -157,6 +173,52 @@ def kronmult_batched_host(matrix_count: int, matrix_size: int, matrix_list_batch
         _addr(output_batched), _addr(workspace_batched), int(nb_batch), int(device))
     if code != 0:
         raise KronmultError(code, "kronmult_batched_host")
+
+
+class Plan:
+    """An aliasing plan (``kronmult_plan_*`` of ``include/kronmult_b200.h``): the batch sorted by output
+    pointer on the device so that items sharing an output are consecutive.  The pointer-array tensors are
+    kept alive by the plan; the data they point to may change between executions."""
+
+    def __init__(self, matrix_count, matrix_size, matrix_list_batched, matrix_stride, input_batched, output_batched,
+                 nb_batch, *, dtype=torch.float64, stream=None):
+        lib = load_library()
+        self._keep = (matrix_list_batched, input_batched, output_batched)
+        self._h = ctypes.c_void_p()
+        handle = 0 if stream is None else (stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream))
+        code = getattr(lib, f"kronmult_plan_create_{_suffix(dtype)}")(
+            int(matrix_count), int(matrix_size), _addr(matrix_list_batched), int(matrix_stride), _addr(input_batched),
+            _addr(output_batched), int(nb_batch), handle, ctypes.byref(self._h))
+        if code != 0:
+            raise KronmultError(code, "kronmult_plan_create")
+
+    def execute(self, stream=None) -> None:
+        handle = 0 if stream is None else (stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream))
+        code = load_library().kronmult_plan_execute(self._h, handle)
+        if code != 0:
+            raise KronmultError(code, "kronmult_plan_execute")
+
+    def stats(self) -> dict:
+        rb, ra, pm = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_int()
+        load_library().kronmult_plan_stats(self._h, ctypes.byref(rb), ctypes.byref(ra), ctypes.byref(pm))
+        return {"runs_before": rb.value, "runs_after": ra.value, "permuted": bool(pm.value)}
+
+    def destroy(self) -> None:
+        if self._h:
+            load_library().kronmult_plan_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def plan_cache_counters() -> "tuple[int, int]":
+    """(hits, builds) of the implicit plans of the blocking entry points."""
+    lib = load_library()
+    return int(lib.kronmult_b200_plan_cache_hits()), int(lib.kronmult_b200_plan_cache_builds())
 
 
 def run_problem(problem, *, stream=None, path: str = "auto") -> None:

@@ -55,6 +55,35 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void *gsrc, unsigned byte
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 
+// mbarrier / TMA wrappers on 32-bit shared-window addresses that are computed once per thread (the generic-pointer
+// wrappers of kernel_regtile.cuh made ptxas re-derive the window base with S2R SR_CgaCtaId at every use)
+__device__ __forceinline__ void mbar_arrive_a(unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx_a(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_a(unsigned dst, const void *gsrc, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+template<typename T>
+__device__ __forceinline__ void cp_async_elem_a(unsigned dst, const T *gsrc)
+{
+    if constexpr (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gsrc) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gsrc) : "memory");
+}
+
 // Two-wide values: a thread works on pairs of independent outputs that share the factor element.  For float the
 // pair operations are the packed FFMA2 / FMUL2 of sm_100 (one issue slot for two FMAs; the scalar operand is
 // broadcast by the instruction itself), for double they are two DFMA / DMUL.
@@ -113,12 +142,19 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
     const bool is_p1      = ((w / IPS) == 0) != swap_roles;
 
     // shared memory of stream q: nothing is shared between streams
-    T *IN          = reinterpret_cast<T *>(smem_raw) + q * (NST * N);                      // [NST][N]   TMA ring
-    T *E           = reinterpret_cast<T *>(smem_raw) + C::IN_EL + q * (NE * 16 * PITCH);   // [NE][16][PITCH]
-    T *MS          = reinterpret_cast<T *>(smem_raw) + C::IN_EL + C::E_EL + q * (NMB * MSTR); // [NMB][MSTR]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (C::IN_EL + C::E_EL + C::MS_EL) * sizeof(T))
-                     + q * (NST + NMB + 2 * NE);
-    uint64_t *full_in = bars, *m_full = bars + NST, *e_full = bars + NST + NMB, *e_empty = bars + NST + NMB + NE;
+    constexpr int NBQ = NST + NMB + 2 * NE;               // mbarriers per stream
+    constexpr unsigned S = sizeof(T);
+    T *IN  = reinterpret_cast<T *>(smem_raw) + q * (NST * N);                          // [NST][N]   TMA ring
+    T *E   = reinterpret_cast<T *>(smem_raw) + C::IN_EL + q * (NE * 16 * PITCH);       // [NE][16][PITCH]
+    T *MS  = reinterpret_cast<T *>(smem_raw) + C::IN_EL + C::E_EL + q * (NMB * MSTR);  // [NMB][MSTR]
+    // the same places as 32-bit shared addresses for the mbarrier / TMA instructions, derived once
+    unsigned sb = (unsigned)__cvta_generic_to_shared(smem_raw);
+    asm volatile("mov.u32 %0, %0;" : "+r"(sb)); // opaque: keeps ptxas from re-deriving the window base per use
+    const unsigned a_in   = sb + q * (NST * N) * S;
+    const unsigned a_ms   = sb + (C::IN_EL + C::E_EL + q * (NMB * MSTR)) * S;
+    const unsigned a_bar  = sb + (C::IN_EL + C::E_EL + C::MS_EL) * S + q * NBQ * 8;
+    const unsigned b_full = a_bar, b_mfull = a_bar + 8 * NST, b_efull = a_bar + 8 * (NST + NMB),
+                   b_eempty = a_bar + 8 * (NST + NMB + NE);
 
     // this CTA's items, split into IPS consecutive streams: stream q takes [kq0, kq0 + cnt)
     const long long K0 = (long long)blockIdx.x * items_per_cta;
@@ -133,9 +169,8 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
 
     if (t < IPS)
     {
-        uint64_t *b = reinterpret_cast<uint64_t *>(smem_raw + (C::IN_EL + C::E_EL + C::MS_EL) * sizeof(T))
-                      + t * (NST + NMB + 2 * NE);
-        for (int i = 0; i < NST + NMB + 2 * NE; ++i) mbar_init(b + i, 1);
+        uint64_t *b = reinterpret_cast<uint64_t *>(smem_raw + (C::IN_EL + C::E_EL + C::MS_EL) * sizeof(T)) + t * NBQ;
+        for (int i = 0; i < NBQ; ++i) mbar_init(b + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -144,64 +179,73 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
     if (is_p1)
     {
         // =================================================================== P1: two slow factors, column-wise
-        // lane j < 5 holds the pointer of factor j; every lane holds the vector pointer
-        auto fac_ptr = [&](int s) -> const T * { return (s < cnt && lane < D) ? A[(kq0 + s) * D + lane] : nullptr; };
-        auto in_ptr  = [&](int s) -> const T * { return (s < cnt) ? in[kq0 + s] : nullptr; };
-        // vector of step s -> ring stage s % NST: one TMA bulk copy when it is 16-byte aligned (lane 0), else
+        // Running pointers into the pointer arrays (three steps ahead of the loop counter): lane j < 5 reads the
+        // pointer of factor j, every lane the vector pointer.
+        const T *const *pa = A + (kq0 * D + (lane < D ? lane : 0));
+        T *const *pin      = in + kq0;
+        auto fac_ptr = [&](int s) -> const T * { return (s < cnt && lane < D) ? pa[(long long)s * D] : nullptr; };
+        auto in_ptr  = [&](int s) -> const T * { return (s < cnt) ? pin[s] : nullptr; };
+        const bool lda4  = (lda == 4);
+        const bool lda16 = ((lda * (int)S) % 16 == 0);
+        // vector of step s (ring stage st) by one TMA bulk copy when it is 16-byte aligned (lane 0), else
         // element-wise cp.async by the whole warp.  Returns true for the element-wise route.
-        auto stage_data = [&](int s, const T *ip) -> bool {
-            if (s >= cnt) return false;
-            T *dst         = IN + (s % NST) * N;
-            const bool tma = aligned16(ip);
+        auto stage_data = [&](bool live, int st, const T *ip) -> bool {
+            if (!live) return false;
+            const unsigned dst = a_in + st * (N * S);
+            const unsigned bar = b_full + 8 * st;
+            const bool tma     = aligned16(ip);
             if (!tma)
             {
 #pragma unroll 8
-                for (int h = 0; h < N / 32; ++h) cp_async_elem<T>(dst + h * 32 + lane, ip + h * 32 + lane);
+                for (int h = 0; h < N / 32; ++h) cp_async_elem_a<T>(dst + (h * 32 + lane) * S, ip + h * 32 + lane);
             }
             if (lane == 0)
             {
                 if (tma)
                 {
                     fence_proxy_async(); // this warp's generic-proxy reads of the stage come first
-                    mbar_arrive_expect_tx(full_in + (s % NST), ITEM_BYTES);
-                    tma_load_1d(dst, ip, ITEM_BYTES, full_in + (s % NST));
+                    mbar_expect_tx_a(bar, ITEM_BYTES);
+                    tma_load_a(dst, ip, ITEM_BYTES, bar);
                 }
-                else mbar_arrive(full_in + (s % NST));
+                else mbar_arrive_a(bar);
             }
             return !tma;
         };
-        // factors of step s -> ring slot s % NMB as five compact column-major 4x4 blocks.  By TMA when the layout
+        // factors of one step -> ring slot ms as five compact column-major 4x4 blocks.  By TMA when the layout
         // allows (one copy per item, per factor or per column), else element-wise.  Returns true for element-wise.
-        auto stage_facs = [&](int s, const T *ap) -> bool {
-            if (s >= cnt) return false;
-            T *dst         = MS + (s % NMB) * MSTR;
-            uint64_t *bar  = m_full + (s % NMB);
+        auto stage_facs = [&](bool live, int ms, const T *ap) -> bool {
+            if (!live) return false;
+            const unsigned dst = a_ms + ms * (MSTR * S);
+            const unsigned bar = b_mfull + 8 * ms;
             const T *ap0   = reinterpret_cast<const T *>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ap), 0));
             const bool a16 = __all_sync(0xffffffffu, lane >= D || aligned16(ap));
             bool elem      = false;
-            if (a16 && lda == 4)
+            if (a16 && lda4)
             {
                 const bool contig = __all_sync(0xffffffffu, lane >= D || ap == ap0 + lane * 16);
                 if (lane == 0)
                 {
                     fence_proxy_async();
-                    mbar_arrive_expect_tx(bar, D * FAC_BYTES);
-                    if (contig) tma_load_1d(dst, ap0, D * FAC_BYTES, bar);
+                    mbar_expect_tx_a(bar, D * FAC_BYTES);
+                    if (contig) tma_load_a(dst, ap0, D * FAC_BYTES, bar);
                 }
-                __syncwarp();
-                if (!contig && lane < D) tma_load_1d(dst + lane * 16, ap, FAC_BYTES, bar);
+                if (!contig)
+                {
+                    __syncwarp();
+                    if (lane < D) tma_load_a(dst + lane * FAC_BYTES, ap, FAC_BYTES, bar);
+                }
             }
-            else if (a16 && (lda * (int)sizeof(T)) % 16 == 0)
+            else if (a16 && lda16)
             {
                 if (lane == 0)
                 {
                     fence_proxy_async();
-                    mbar_arrive_expect_tx(bar, D * FAC_BYTES);
+                    mbar_expect_tx_a(bar, D * FAC_BYTES);
                 }
                 __syncwarp();
                 const T *apj = reinterpret_cast<const T *>(
                     __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ap), (lane >> 2) % D));
-                if (lane < 4 * D) tma_load_1d(dst + lane * 4, apj + (long long)(lane & 3) * lda, COL_BYTES, bar);
+                if (lane < 4 * D) tma_load_a(dst + lane * COL_BYTES, apj + (long long)(lane & 3) * lda, COL_BYTES, bar);
             }
             else
             {
@@ -212,9 +256,9 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
                     const int e  = lane + 32 * i; // element e = factor e/16, column (e%16)/4, row e%4
                     const T *apj = reinterpret_cast<const T *>(
                         __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ap), (e >> 4) % D));
-                    if (e < D * 16) cp_async_elem<T>(dst + e, apj + (e & 3) + (long long)((e >> 2) & 3) * lda);
+                    if (e < D * 16) cp_async_elem_a<T>(dst + e * S, apj + (e & 3) + (long long)((e >> 2) & 3) * lda);
                 }
-                if (lane == 0) mbar_arrive(bar);
+                if (lane == 0) mbar_arrive_a(bar);
             }
             return elem;
         };
@@ -225,22 +269,24 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
         // prologue: vector of step 0, L2 pull of step 1, factors of steps 0 and 1
         const T *ip_b = in_ptr(1), *ip_c = in_ptr(2);   // inside the loop: vectors of steps s+1 and s+2
         const T *ap_c = fac_ptr(2);                     //                  factor pointers of step s+2
-        bool el_0 = stage_data(0, in_ptr(0));           // element-wise copies in flight for step s ...
-        el_0 |= stage_facs(0, fac_ptr(0));
-        bool el_1 = stage_facs(1, fac_ptr(1));          // ... and for step s+1
+        bool el_0 = stage_data(true, 0, in_ptr(0));     // element-wise copies in flight for step s ...
+        el_0 |= stage_facs(true, 0, fac_ptr(0));
+        bool el_1 = stage_facs(cnt > 1, 1, fac_ptr(1)); // ... and for step s+1
         l2_pull(ip_b);
         cp_async_commit();
+        int ms = 0, ms2 = 2;            // factor ring slots of step s and of step s+2
+        unsigned mph = 0;               // phase parity of slot ms
 
         for (int s = 0; s < cnt; ++s)
         {
-            const int st = s % NST;
+            const int st = s & 1;
             const T *ip_d = in_ptr(s + 3);       // pointer pipeline: fetched now, used next step
             const T *ap_d = fac_ptr(s + 3);
 
             // the stage and the factor slot written below were last read in step s-1 / s-3 by this warp and in
             // step s-3 by its P2 warp, which ended before this warp passed e_empty in step s-1
-            bool el_2 = stage_facs(s + 2, ap_c);
-            el_1 |= stage_data(s + 1, ip_b);
+            bool el_2 = stage_facs(s + 2 < cnt, ms2, ap_c);
+            el_1 |= stage_data(s + 1 < cnt, st ^ 1, ip_b);
             cp_async_commit();
             l2_pull(ip_c);                       // step s+2; its pointer was fetched a step ago
             if (el_0)
@@ -250,8 +296,8 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
                 asm volatile("cp.async.wait_group 1;" ::: "memory");
                 __syncwarp();
             }
-            mbar_wait(full_in + st, (unsigned)(s / NST) & 1u);
-            mbar_wait(m_full + (s % NMB), (unsigned)(s / NMB) & 1u);
+            mbar_wait_a(b_full + 8 * st, (unsigned)(s >> 1) & 1u);
+            mbar_wait_a(b_mfull + 8 * ms, mph);
 
             using P = typename V2<T>::type;
             P x[16]; // x[h] = my two adjacent columns of row h = (i0, i1)
@@ -259,23 +305,25 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
                 const T *src = IN + st * N + 2 * lane;
 #pragma unroll
                 for (int h = 0; h < 16; ++h) x[h] = *reinterpret_cast<const P *>(src + h * 64);
-                const T *Ms = MS + (s % NMB) * MSTR;
+                const T *Ms = MS + ms * MSTR;
                 T m1[16], m0[16];
                 lds16<T>(Ms + 1 * 16, m1);
                 lds16<T>(Ms + 0 * 16, m0);
                 tile16_apply_cm2<T, 1>(x, m1);
                 tile16_apply_cm2<T, 4>(x, m0);
             }
-            const int eb = s % NE;
+            const int eb = s & 1;
             T *Eb        = E + eb * 16 * PITCH;
-            mbar_wait(e_empty + eb, (((unsigned)(s / NE)) & 1u) ^ 1u); // first use passes on a fresh barrier
+            mbar_wait_a(b_eempty + 8 * eb, (((unsigned)(s >> 1)) & 1u) ^ 1u); // first use passes on a fresh barrier
 #pragma unroll
             for (int h = 0; h < 16; ++h) *reinterpret_cast<P *>(Eb + h * PITCH + 2 * lane) = x[h];
             __syncwarp();
-            if (lane == 0) mbar_arrive(e_full + eb);
+            if (lane == 0) mbar_arrive_a(b_efull + 8 * eb);
 
             ip_b = ip_c; ip_c = ip_d; ap_c = ap_d;
             el_0 = el_1; el_1 = el_2;
+            if (++ms == NMB) { ms = 0; mph ^= 1u; }
+            if (++ms2 == NMB) ms2 = 0;
         }
     }
     else
@@ -286,18 +334,21 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
         P acc[16]; // acc[i2' * 4 + i3'] = the pair i4' = 2 hf, 2 hf + 1
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i].x = acc[i].y = T(0);
-        T *o_cur  = out[kq0];
-        T *o_next = (cnt > 1) ? out[kq0 + 1] : nullptr; // output pointers are fetched two steps ahead
+        T *const *pout = out + kq0;
+        T *o_cur  = pout[0];
+        T *o_next = (cnt > 1) ? pout[1] : nullptr; // output pointers are fetched two steps ahead
+        int ms = 0;
+        unsigned mph = 0;
 
         for (int s = 0; s < cnt; ++s)
         {
-            T *o_next2   = (s + 2 < cnt) ? out[kq0 + s + 2] : nullptr;
-            const int eb = s % NE;
+            T *o_next2   = (s + 2 < cnt) ? pout[s + 2] : nullptr;
+            const int eb = s & 1;
             T *Eb        = E + eb * 16 * PITCH;
             T *erow      = Eb + row * PITCH;
-            const T *Mq  = MS + (s % NMB) * MSTR;
-            mbar_wait(e_full + eb, (unsigned)(s / NE) & 1u);
-            mbar_wait(m_full + (s % NMB), (unsigned)(s / NMB) & 1u); // complete long ago: makes the TMA writes visible here
+            const T *Mq  = MS + ms * MSTR;
+            mbar_wait_a(b_efull + 8 * eb, (unsigned)(s >> 1) & 1u);
+            mbar_wait_a(b_mfull + 8 * ms, mph); // complete long ago: makes the TMA writes visible here
             {
                 // f4[k] = (F4(2hf, k), F4(2hf+1, k)): my two rows of the fastest factor; f3: the second fastest
                 P f4[4];
@@ -365,9 +416,10 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(e_empty + eb); // every read of E and of this step's factors is done
+            if (lane == 0) mbar_arrive_a(b_eempty + 8 * eb); // every read of E and of this step's factors is done
             o_cur  = o_next;
             o_next = o_next2;
+            if (++ms == NMB) { ms = 0; mph ^= 1u; }
         }
     }
 }

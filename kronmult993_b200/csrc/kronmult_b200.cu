@@ -304,13 +304,45 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
     return run_generic<T>(di, d, n, A, lda, in, out, nb, st);
 }
 
+} // namespace kron
+
+#include "planner.cuh"
+
+namespace kron
+{
+
 template<typename T>
 static int blocking_call(int d, int n, const T *const *A, int lda, T **in, T **out, int nb)
 {
     // legacy default stream + device-wide synchronisation, as kronmult.cu:191-196
-    cudaError_t e = dispatch<T>(d, n, A, lda, in, out, nb, cudaStreamLegacy);
+    bool handled  = false;
+    cudaError_t e = autoplan_call<T>(d, n, A, lda, in, out, nb, cudaStreamLegacy, handled);
+    if (!handled) e = dispatch<T>(d, n, A, lda, in, out, nb, cudaStreamLegacy);
     cudaError_t s = cudaDeviceSynchronize();
     return (int)(e != cudaSuccess ? e : s);
+}
+
+template<typename T>
+static int plan_create(int d, int n, const T *const *A, int lda, T **in, T **out, int nb, cudaStream_t st,
+                       kronmult_plan **plan)
+{
+    if (!plan) return (int)cudaErrorInvalidValue;
+    *plan = nullptr;
+    if (nb < 0 || d < 0 || n < 1 || lda < n || (nb > 0 && ((!A && d > 0) || !in || !out))) return (int)cudaErrorInvalidValue;
+    DeviceInfo di;
+    cudaError_t e = device_info(di);
+    if (e != cudaSuccess) return (int)e;
+    Plan *p = new Plan;
+    p->elem = (int)sizeof(T); p->d = d; p->n = n; p->lda = lda; p->nb = nb;
+    cudaGetDevice(&p->device);
+    p->A0 = A; p->in0 = in; p->out0 = out;
+    if (nb > 0)
+    {
+        e = plan_build(*p, di.sms, st, nullptr);
+        if (e != cudaSuccess) { delete p; return (int)e; }
+    }
+    *plan = reinterpret_cast<kronmult_plan *>(p);
+    return 0;
 }
 
 } // namespace kron
@@ -354,12 +386,47 @@ int kronmult_batched_f32_async(int d, int n, const float *const *A, int lda, flo
     return (int)kron::dispatch<float>(d, n, A, lda, in, out, nb, static_cast<cudaStream_t>(stream));
 }
 
+int kronmult_plan_create_f64(int d, int n, const double *const *A, int lda, double **in, double **out, int nb,
+                             void *stream, kronmult_plan **plan)
+{
+    return kron::plan_create<double>(d, n, A, lda, in, out, nb, static_cast<cudaStream_t>(stream), plan);
+}
+int kronmult_plan_create_f32(int d, int n, const float *const *A, int lda, float **in, float **out, int nb,
+                             void *stream, kronmult_plan **plan)
+{
+    return kron::plan_create<float>(d, n, A, lda, in, out, nb, static_cast<cudaStream_t>(stream), plan);
+}
+int kronmult_plan_execute(const kronmult_plan *plan, void *stream)
+{
+    if (!plan) return (int)cudaErrorInvalidValue;
+    const kron::Plan &p = *reinterpret_cast<const kron::Plan *>(plan);
+    cudaStream_t st     = static_cast<cudaStream_t>(stream);
+    return (int)(p.elem == 8 ? kron::plan_execute<double>(p, st) : kron::plan_execute<float>(p, st));
+}
+int kronmult_plan_stats(const kronmult_plan *plan, long long *runs_before, long long *runs_after, int *permuted)
+{
+    if (!plan) return (int)cudaErrorInvalidValue;
+    const kron::Plan &p = *reinterpret_cast<const kron::Plan *>(plan);
+    if (runs_before) *runs_before = (long long)p.before.runs;
+    if (runs_after) *runs_after = (long long)p.runs_after;
+    if (permuted) *permuted = p.permuted ? 1 : 0;
+    return 0;
+}
+int kronmult_plan_destroy(kronmult_plan *plan)
+{
+    delete reinterpret_cast<kron::Plan *>(plan);
+    return 0;
+}
+long long kronmult_b200_plan_cache_hits(void) { return kron::g_plan_hits.load(); }
+long long kronmult_b200_plan_cache_builds(void) { return kron::g_plan_builds.load(); }
+
 const char *kronmult_b200_version(void) { return "kronmult993_b200 0.1 (sm_100a)"; }
 long long kronmult_b200_launch_count(void) { return kron::g_launches.load(); }
 const char *kronmult_b200_last_path(void) { return kron::t_last_path; }
 int kronmult_b200_set_tuning(int knob, int value)
 {
     if (knob == 0) { kron::g_regtile_stage.store(value); return 0; }
+    if (knob == 1) { kron::g_autoplan.store(value); return 0; }
     return (int)cudaErrorInvalidValue;
 }
 int kronmult_b200_force_path(int path)

@@ -204,3 +204,78 @@ def test_repeated_calls_accumulate(kron, oracle_mod):
     twice = p.out_slab
     d1, d2 = (once - out0), (twice - out0)
     assert float(torch.linalg.norm(d2 - 2 * d1) / torch.linalg.norm(d1)) < 1e-13
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("n,d,nb,r", [(4, 5, 3000, 30), (4, 6, 300, 10), (8, 4, 400, 8), (6, 3, 5000, 25), (4, 4, 6000, 16)])
+def test_explicit_plan_on_shuffled_batches(kron, oracle_mod, n, d, nb, r, dt):
+    """kronmult_plan_*: a batch whose equal output pointers are scattered is sorted by output pointer; the
+    result is the same sum (within tolerance), the number of runs drops to the number of outputs."""
+    hp = batch.make_problem(d, n, nb, dt, "cpu", seed=n + d, alias="shuffled", items_per_output=r, lda=n + 2).to_host()
+    p = batch.from_host(hp, "cuda")
+    A, i, o, w = p.pointer_arrays()
+    plan = kron.Plan(d, n, A, p.lda, i, o, nb, dtype=dt)
+    st = plan.stats()
+    assert st["permuted"] and st["runs_after"] == (nb + r - 1) // r and st["runs_before"] > 2 * st["runs_after"]
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    plan.execute(s)
+    s.synchronize()
+    exp = oracle_mod.run(hp, "oracle", threads=1)
+    assert oracle_mod.rel_l2(p.out_slab.cpu().numpy(), exp) <= _tol(hp)
+    # the data may change between executions of the same plan: run again on new inputs (outputs keep accumulating)
+    p.in_slab.mul_(-2.0)
+    plan.execute(s)
+    s.synchronize()
+    got2 = p.out_slab.cpu().numpy()
+    exp2 = 2 * hp.out_slab - exp  # out0 + P - 2 P
+    assert oracle_mod.rel_l2(got2, exp2) <= 10 * _tol(hp)
+    plan.destroy()
+
+
+def test_plan_keeps_grouped_batches_as_they_are(kron, oracle_mod):
+    hp = batch.make_problem(5, 4, 2000, torch.float64, "cpu", seed=3, alias="runs", items_per_output=32).to_host()
+    p = batch.from_host(hp, "cuda")
+    A, i, o, w = p.pointer_arrays()
+    plan = kron.Plan(5, 4, A, p.lda, i, o, 2000)
+    st = plan.stats()
+    assert not st["permuted"] and st["runs_before"] == 63
+    plan.execute()
+    torch.cuda.synchronize()
+    assert oracle_mod.rel_l2(p.out_slab.cpu().numpy(), oracle_mod.run(hp, "oracle", threads=1)) <= 1e-12
+    # an empty plan is a no-op
+    kron.Plan(5, 4, A, p.lda, i, o, 0).execute()
+
+
+def test_blocking_entry_plans_shuffled_batches_once(kron, oracle_mod):
+    """The drop-in blocking call builds a plan for a scattered batch and reuses it while the pointer arrays stay
+    the same; changing one output pointer is detected by the content hash."""
+    nb = 8192
+    hp = batch.make_problem(5, 4, nb, torch.float64, "cpu", seed=17, alias="shuffled", items_per_output=16).to_host()
+    p = batch.from_host(hp, "cuda")
+    A, i, o, w = p.pointer_arrays()
+    h0, b0 = kron.plan_cache_counters()
+    kron.kronmult_batched(5, 4, A, p.lda, i, o, w, nb)
+    exp = oracle_mod.run(hp, "oracle", threads=1)
+    assert oracle_mod.rel_l2(p.out_slab.cpu().numpy(), exp) <= 1e-12
+    h1, b1 = kron.plan_cache_counters()
+    assert (h1 - h0, b1 - b0) == (0, 1)
+    kron.kronmult_batched(5, 4, A, p.lda, i, o, w, nb)
+    h2, b2 = kron.plan_cache_counters()
+    assert (h2 - h1, b2 - b1) == (1, 0)
+    o[5] = o[6]  # same array, different content -> a new plan, and still the right answer
+    hp.out_off[5] = hp.out_off[6]
+    before = p.out_slab.cpu().numpy().copy()
+    kron.kronmult_batched(5, 4, A, p.lda, i, o, w, nb)
+    h3, b3 = kron.plan_cache_counters()
+    assert (h3 - h2, b3 - b2) == (0, 1)
+    hp.out_slab[:] = before
+    exp3 = oracle_mod.run(hp, "oracle", threads=1)
+    assert oracle_mod.rel_l2(p.out_slab.cpu().numpy(), exp3) <= 1e-12
+    # knob 1 switches implicit planning off
+    kron.set_tuning(1, 0)
+    try:
+        kron.kronmult_batched(5, 4, A, p.lda, i, o, w, nb)
+        assert kron.plan_cache_counters() == (h3, b3)
+    finally:
+        kron.set_tuning(1, 1)

@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--fp64-tflops", type=float, default=37.0)
     ap.add_argument("--fp32-tflops", type=float, default=75.0)
     ap.add_argument("--alias", default=None)
+    ap.add_argument("--plan", action="store_true", help="build an aliasing plan first and time its execution")
     ap.add_argument("--telemetry", action="store_true", help="NVML SM clock / power after every rep")
     ap.add_argument("--tune", default=None, help="knob=value[,knob=value] for kronmult_b200_set_tuning")
     args = ap.parse_args()
@@ -70,11 +71,20 @@ def main():
         api.force_path(args.path)
         torch.cuda.synchronize()  # the problem was built on the default stream
         times, tele = [], []
+        plan, plan_info = None, {}
+        if args.plan:
+            import time
+            t0 = time.perf_counter()
+            plan = api.Plan(p.d, p.n, A, p.lda, i, o, p.nb, dtype=dt)
+            plan_info = {"plan_build_ms": round((time.perf_counter() - t0) * 1e3, 3), **plan.stats()}
         with torch.cuda.stream(stream):
             for rep in range(args.reps + 2):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
-                api.kronmult_batched(p.d, p.n, A, p.lda, i, o, w, p.nb, dtype=dt, stream=stream)
+                if plan is not None:
+                    plan.execute(stream)
+                else:
+                    api.kronmult_batched(p.d, p.n, A, p.lda, i, o, w, p.nb, dtype=dt, stream=stream)
                 e1.record(stream)
                 e1.synchronize()
                 if rep >= 2:
@@ -91,7 +101,7 @@ def main():
                           "ms_all": [round(x, 4) for x in times], "gflops": round(fl / t * 1e-9, 1),
                           "alg_gbs": round(by / t * 1e-9, 1), "roofline_ms": round(roof * 1e3, 4),
                           "frac": round(roof / t, 4), "bound": "hbm" if by / (hbm * 1e9) >= fl / peak else "fp",
-                          **({"sm_mhz_power_w": tele} if tele else {})}),
+                          **plan_info, **({"sm_mhz_power_w": tele} if tele else {})}),
               flush=True)
         del p, A, i, o, w
         torch.cuda.empty_cache()
