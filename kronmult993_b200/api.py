@@ -76,7 +76,9 @@ def load_library() -> ctypes.CDLL:
     if _lib is not None:
         return _lib
     path = _build.LIB
-    if os.environ.get("KRONMULT_B200_NO_BUILD") != "1":
+    if os.environ.get("KRONMULT_B200_LIB"):  # A/B experiments: an alternative build of the same library
+        path = os.environ["KRONMULT_B200_LIB"]
+    elif os.environ.get("KRONMULT_B200_NO_BUILD") != "1":
         try:
             path = _build.build_library()
         except Exception:

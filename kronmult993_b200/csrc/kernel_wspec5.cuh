@@ -121,7 +121,7 @@ __device__ __forceinline__ void tile16_apply_cm2(typename V2<T>::type (&x)[16], 
     }
 }
 
-template<typename T>
+template<typename T, int dbg>
 __global__ void __launch_bounds__(Wspec5<T>::THREADS, Wspec5<T>::MINB)
 kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T *const *__restrict__ out,
                    const int lda, const int nb, const long long items_per_cta, const int sms)
@@ -132,9 +132,11 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
     constexpr unsigned ITEM_BYTES = N * sizeof(T), FAC_BYTES = 16 * sizeof(T), COL_BYTES = 4 * sizeof(T);
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int t    = threadIdx.x;
-    const int lane = t & 31;
-    const int w    = t >> 5;
+    const int t = threadIdx.x;
+    int lane, w;
+    // opaque copies: ptxas otherwise re-reads SR_TID (20+ cycles each) wherever registers are tight
+    asm volatile("mov.u32 %0, %1;" : "=r"(lane) : "r"(t & 31));
+    asm volatile("mov.u32 %0, %1;" : "=r"(w) : "r"(t >> 5));
     // Warp w runs on SM sub-partition w % 4.  Co-resident CTAs swap the roles of their warp pairs so that every
     // sub-partition hosts P1 and P2 warps.
     const bool swap_roles = ((blockIdx.x / sms) & 1) != 0;
@@ -203,7 +205,9 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
             {
                 if (tma)
                 {
-                    fence_proxy_async(); // this warp's generic-proxy reads of the stage come first
+                    // No proxy fence: this warp's reads of the stage (step s-1) have returned -- their values were
+                    // consumed before the __syncwarp that ended that step -- so the bulk copy cannot overtake them.
+                    if constexpr ((dbg & 16) != 0) fence_proxy_async();
                     mbar_expect_tx_a(bar, ITEM_BYTES);
                     tma_load_a(dst, ip, ITEM_BYTES, bar);
                 }
@@ -225,7 +229,9 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
                 const bool contig = __all_sync(0xffffffffu, lane >= D || ap == ap0 + lane * 16);
                 if (lane == 0)
                 {
-                    fence_proxy_async();
+                    // the slot's last readers (this warp and its P2 warp, step s-3) are ordered before this point by
+                    // the e_empty mbarrier this thread waited on in step s-1
+                    if constexpr ((dbg & 16) != 0) fence_proxy_async();
                     mbar_expect_tx_a(bar, D * FAC_BYTES);
                     if (contig) tma_load_a(dst, ap0, D * FAC_BYTES, bar);
                 }
@@ -239,7 +245,7 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
             {
                 if (lane == 0)
                 {
-                    fence_proxy_async();
+                    if constexpr ((dbg & 16) != 0) fence_proxy_async();
                     mbar_expect_tx_a(bar, D * FAC_BYTES);
                 }
                 __syncwarp();
@@ -309,8 +315,12 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
                 T m1[16], m0[16];
                 lds16<T>(Ms + 1 * 16, m1);
                 lds16<T>(Ms + 0 * 16, m0);
-                tile16_apply_cm2<T, 1>(x, m1);
-                tile16_apply_cm2<T, 4>(x, m0);
+                if constexpr ((dbg & 8) == 0)
+                {
+                    tile16_apply_cm2<T, 1>(x, m1);
+                    tile16_apply_cm2<T, 4>(x, m0);
+                }
+                else x[0].x += m1[0] + m0[0];
             }
             const int eb = s & 1;
             T *Eb        = E + eb * 16 * PITCH;
@@ -361,6 +371,17 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
                 {
                     T x[16], f2[4];
                     lds16<T>(erow + j * 16, x);
+                    if constexpr ((dbg & 1) != 0)
+                    {
+                        // energy experiment: one more pass over the row slice (results discarded)
+                        const unsigned a = (unsigned)__cvta_generic_to_shared(erow + j * 16);
+#pragma unroll
+                        for (int c = 0; c < 16 * (int)sizeof(T) / 16; ++c)
+                        {
+                            unsigned r0, r1, r2, r3;
+                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a + 16 * c));
+                        }
+                    }
                     // fastest index: y[i3] = sum_k x[i3][k] F4(2hf + {0,1}, k)
                     P y[4];
 #pragma unroll
@@ -389,10 +410,25 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
                         const float4 v = *reinterpret_cast<const float4 *>(Mq + 2 * 16 + j * 4);
                         f2[0] = v.x; f2[1] = v.y; f2[2] = v.z; f2[3] = v.w;
                     }
+                    if constexpr ((dbg & 4) != 0)
+                    {
+                        // energy experiment: no arithmetic to speak of in P2 (wrong results)
 #pragma unroll
-                    for (int i2 = 0; i2 < 4; ++i2)
+                        for (int m = 0; m < 4; ++m) acc[m].x += x[m] + x[4 + m] + x[8 + m] + x[12 + m] + f2[m];
+                    }
+                    else if constexpr ((dbg & 2) != 0)
+                    {
+                        // energy experiment: a quarter of the third factor's FMAs only (wrong results)
 #pragma unroll
-                        for (int m = 0; m < 4; ++m) acc[i2 * 4 + m] = pfma(z[m], f2[i2], acc[i2 * 4 + m]);
+                        for (int m = 0; m < 4; ++m) acc[m] = pfma(z[m], f2[0], acc[m]);
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int i2 = 0; i2 < 4; ++i2)
+#pragma unroll
+                            for (int m = 0; m < 4; ++m) acc[i2 * 4 + m] = pfma(z[m], f2[i2], acc[i2 * 4 + m]);
+                    }
                 }
             }
             // ---- flush when the run of equal output pointers ends here: the accumulators go back into the rows
@@ -424,14 +460,25 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
     }
 }
 
+static std::atomic<int> g_wspec5_dbg{0}; // knob 2 of kronmult_b200_set_tuning: ablation variants (-DKRON_WSPEC5_EXPERIMENTS)
+
 template<typename T>
 static cudaError_t launch_wspec5(int sms, const T *const *A, int lda, T *const *in, T *const *out, int nb,
                                  cudaStream_t st, std::atomic<long long> &launches)
 {
     using C  = Wspec5<T>;
-    auto kfn = kron_wspec5_kernel<T>;
-    static int ctas_per_sm = 0; // benign race: idempotent
-    if (ctas_per_sm == 0)
+    const int dbg = g_wspec5_dbg.load(std::memory_order_relaxed);
+#ifdef KRON_WSPEC5_EXPERIMENTS
+    // ablation variants behind knob 2 (profiles/ablation_wspec5_r01.md): 1 = extra shared-memory pass in P2,
+    // 2 = 15 % fewer FMAs, 4 / 8 / 12 = no arithmetic in P2 / P1 / both, 16 = proxy fences before every TMA copy
+    auto kfn = dbg == 1 ? kron_wspec5_kernel<T, 1> : dbg == 2 ? kron_wspec5_kernel<T, 2> : dbg == 4 ? kron_wspec5_kernel<T, 4>
+             : dbg == 8 ? kron_wspec5_kernel<T, 8> : dbg == 12 ? kron_wspec5_kernel<T, 12> : dbg == 16 ? kron_wspec5_kernel<T, 16>
+             : kron_wspec5_kernel<T, 0>;
+#else
+    auto kfn = kron_wspec5_kernel<T, 0>;
+#endif
+    static int ctas_per_sm = 0, dbg_seen = -1;
+    if (ctas_per_sm == 0 || dbg_seen != dbg)
     {
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         if (e != cudaSuccess) return e;
@@ -439,6 +486,7 @@ static cudaError_t launch_wspec5(int sms, const T *const *A, int lda, T *const *
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, C::THREADS, C::SMEM);
         if (e != cudaSuccess) return e;
         ctas_per_sm = occ > 0 ? occ : 1;
+        dbg_seen    = dbg;
     }
     long long grid = (long long)sms * ctas_per_sm;
     long long ipc  = ((long long)nb + grid - 1) / grid; // items per CTA

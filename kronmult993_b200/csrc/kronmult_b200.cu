@@ -427,6 +427,7 @@ int kronmult_b200_set_tuning(int knob, int value)
 {
     if (knob == 0) { kron::g_regtile_stage.store(value); return 0; }
     if (knob == 1) { kron::g_autoplan.store(value); return 0; }
+    if (knob == 2) { kron::g_wspec5_dbg.store(value); return 0; }
     return (int)cudaErrorInvalidValue;
 }
 int kronmult_b200_force_path(int path)
