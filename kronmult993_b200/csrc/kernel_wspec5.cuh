@@ -15,10 +15,11 @@
 //   * an item's flush is the business of ONE warp (__syncwarp, no named barrier);
 //   * a CTA is IPS independent pipelines (P1 warp q -> P2 warp q) that share nothing: every mbarrier has one
 //     producer warp and one consumer warp, there is no CTA-wide or named barrier in the loop;
-//   * whole items are pulled into L2 two steps ahead with one cp.async.bulk.prefetch.L2 each, the TMA copy into
-//     the 2-stage ring follows one step ahead; the five factors of an item are staged two steps ahead (5-deep
-//     ring) by TMA as well -- one 640-byte copy when they are contiguous (dense batches), one per factor or per
-//     column otherwise, element-wise cp.async only when alignment rules TMA out;
+//   * whole items are pulled into L2 two steps ahead with one cp.async.bulk.prefetch.L2 each; the TMA copy into
+//     the 2-stage ring follows one step ahead and brings the item's five factors along on the same mbarrier --
+//     one 640-byte copy when they are contiguous (dense batches), one per factor or per column otherwise,
+//     element-wise cp.async only when alignment rules TMA out.  P1 forwards the three fast factors to P2 inside
+//     the exchange buffer, so P2 waits on one mbarrier per step and P1 on two;
 // Per output element the products are accumulated k ascending from 0 like multiply_transpose
 // (kronmult.cu:66-70); factors are applied slowest index first.
 #pragma once
@@ -39,15 +40,15 @@ struct Wspec5
     static constexpr int PITCH   = 64 + 16 / (int)sizeof(T);       // padded row of E, in elements
     static constexpr int NE      = 2;                              // exchange buffers per stream
     static constexpr int NST     = 2;                              // TMA ring stages per stream
-    static constexpr int NMB     = 5;                              // factor ring depth (see the P1 loop)
     static constexpr int MINB    = (sizeof(T) == 4) ? 4 : 3;       // resident CTAs per SM aimed at
-    static constexpr int MSTR    = D * 16;                         // per-item factor block: 5 column-major 4x4
+    static constexpr int MSTR    = D * 16;                         // an item's factors: 5 column-major 4x4 blocks
+    static constexpr int STG     = N + MSTR;                       // ring stage: the vector, then its factors
+    static constexpr int EBUF    = 16 * PITCH + 3 * 16;            // exchange buffer: 16 rows, then factors 2..4 for P2
     static constexpr int THREADS = 64 * IPS;
-    static constexpr int IN_EL   = IPS * NST * N;
-    static constexpr int E_EL    = IPS * NE * 16 * PITCH;
-    static constexpr int MS_EL   = IPS * NMB * MSTR;
-    static constexpr int NBAR    = IPS * (NST + NMB + 2 * NE);
-    static constexpr int SMEM    = (IN_EL + E_EL + MS_EL) * (int)sizeof(T) + 8 * NBAR + 16;
+    static constexpr int IN_EL   = IPS * NST * STG;
+    static constexpr int E_EL    = IPS * NE * EBUF;
+    static constexpr int NBQ     = NST + 2 * NE;                   // mbarriers per stream
+    static constexpr int SMEM    = (IN_EL + E_EL) * (int)sizeof(T) + 8 * IPS * NBQ + 16;
 };
 
 __device__ __forceinline__ void l2_prefetch_bulk(const void *gsrc, unsigned bytes)
@@ -127,8 +128,7 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
                    const int lda, const int nb, const long long items_per_cta, const int sms)
 {
     using C = Wspec5<T>;
-    constexpr int D = 5, N = C::N, IPS = C::IPS, PITCH = C::PITCH, NMB = C::NMB, NE = C::NE, NST = C::NST;
-    constexpr int MSTR = C::MSTR;
+    constexpr int D = 5, N = C::N, IPS = C::IPS, PITCH = C::PITCH, NE = C::NE, NST = C::NST;
     constexpr unsigned ITEM_BYTES = N * sizeof(T), FAC_BYTES = 16 * sizeof(T), COL_BYTES = 4 * sizeof(T);
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -144,19 +144,16 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
     const bool is_p1      = ((w / IPS) == 0) != swap_roles;
 
     // shared memory of stream q: nothing is shared between streams
-    constexpr int NBQ = NST + NMB + 2 * NE;               // mbarriers per stream
+    constexpr int NBQ = C::NBQ, STG = C::STG, EBUF = C::EBUF;
     constexpr unsigned S = sizeof(T);
-    T *IN  = reinterpret_cast<T *>(smem_raw) + q * (NST * N);                          // [NST][N]   TMA ring
-    T *E   = reinterpret_cast<T *>(smem_raw) + C::IN_EL + q * (NE * 16 * PITCH);       // [NE][16][PITCH]
-    T *MS  = reinterpret_cast<T *>(smem_raw) + C::IN_EL + C::E_EL + q * (NMB * MSTR);  // [NMB][MSTR]
+    T *IN  = reinterpret_cast<T *>(smem_raw) + q * (NST * STG);               // [NST][STG]  TMA ring
+    T *E   = reinterpret_cast<T *>(smem_raw) + C::IN_EL + q * (NE * EBUF);    // [NE][EBUF]  exchange buffers
     // the same places as 32-bit shared addresses for the mbarrier / TMA instructions, derived once
     unsigned sb = (unsigned)__cvta_generic_to_shared(smem_raw);
     asm volatile("mov.u32 %0, %0;" : "+r"(sb)); // opaque: keeps ptxas from re-deriving the window base per use
-    const unsigned a_in   = sb + q * (NST * N) * S;
-    const unsigned a_ms   = sb + (C::IN_EL + C::E_EL + q * (NMB * MSTR)) * S;
-    const unsigned a_bar  = sb + (C::IN_EL + C::E_EL + C::MS_EL) * S + q * NBQ * 8;
-    const unsigned b_full = a_bar, b_mfull = a_bar + 8 * NST, b_efull = a_bar + 8 * (NST + NMB),
-                   b_eempty = a_bar + 8 * (NST + NMB + NE);
+    const unsigned a_in   = sb + q * (NST * STG) * S;
+    const unsigned a_bar  = sb + (C::IN_EL + C::E_EL) * S + q * NBQ * 8;
+    const unsigned b_full = a_bar, b_efull = a_bar + 8 * NST, b_eempty = a_bar + 8 * (NST + NE);
 
     // this CTA's items, split into IPS consecutive streams: stream q takes [kq0, kq0 + cnt)
     const long long K0 = (long long)blockIdx.x * items_per_cta;
@@ -171,7 +168,7 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
 
     if (t < IPS)
     {
-        uint64_t *b = reinterpret_cast<uint64_t *>(smem_raw + (C::IN_EL + C::E_EL + C::MS_EL) * sizeof(T)) + t * NBQ;
+        uint64_t *b = reinterpret_cast<uint64_t *>(smem_raw + (C::IN_EL + C::E_EL) * sizeof(T)) + t * NBQ;
         for (int i = 0; i < NBQ; ++i) mbar_init(b + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -181,140 +178,118 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
     if (is_p1)
     {
         // =================================================================== P1: two slow factors, column-wise
-        // Running pointers into the pointer arrays (three steps ahead of the loop counter): lane j < 5 reads the
-        // pointer of factor j, every lane the vector pointer.
-        const T *const *pa = A + (kq0 * D + (lane < D ? lane : 0));
-        T *const *pin      = in + kq0;
-        auto fac_ptr = [&](int s) -> const T * { return (s < cnt && lane < D) ? pa[(long long)s * D] : nullptr; };
-        auto in_ptr  = [&](int s) -> const T * { return (s < cnt) ? pin[s] : nullptr; };
+        // Running pointers into the pointer arrays: lane j < 5 reads the pointer of factor j (and every lane that of
+        // factor 0, to test contiguity without a shuffle), every lane the vector pointer.
+        const T *const *pa  = A + (kq0 * D + (lane < D ? lane : 0));
+        const T *const *pa0 = A + kq0 * D;
+        T *const *pin       = in + kq0;
         const bool lda4  = (lda == 4);
         const bool lda16 = ((lda * (int)S) % 16 == 0);
-        // vector of step s (ring stage st) by one TMA bulk copy when it is 16-byte aligned (lane 0), else
-        // element-wise cp.async by the whole warp.  Returns true for the element-wise route.
-        auto stage_data = [&](bool live, int st, const T *ip) -> bool {
+        // Vector and factors of one step -> ring stage st, completion on ONE mbarrier.  By TMA where alignment allows
+        // (vector: one bulk copy; factors: one copy per item when the five blocks are contiguous -- dense batches --
+        // else one per factor or per column), element-wise cp.async otherwise.  Returns true if any element-wise
+        // copy was issued (the consumer then also waits for its cp.async group).
+        // No proxy fence: this warp's reads of the stage (step s-1) have returned -- their values were consumed
+        // before the __syncwarp that ended that step -- so the bulk copies cannot overtake them.
+        auto stage_step = [&](bool live, int st, const T *ip, const T *ap, const T *ap0) -> bool {
             if (!live) return false;
-            const unsigned dst = a_in + st * (N * S);
+            const unsigned dst = a_in + st * (STG * S), fdst = dst + N * S;
             const unsigned bar = b_full + 8 * st;
-            const bool tma     = aligned16(ip);
-            if (!tma)
+            const bool vtma    = aligned16(ip);
+            // fast path: five 16-byte aligned factor blocks back to back
+            const bool contig  = lda4 && aligned16(ap0) && __all_sync(0xffffffffu, lane >= D || ap == ap0 + lane * 16);
+            bool elem = !vtma;
+            if (!vtma)
             {
 #pragma unroll 8
                 for (int h = 0; h < N / 32; ++h) cp_async_elem_a<T>(dst + (h * 32 + lane) * S, ip + h * 32 + lane);
             }
-            if (lane == 0)
-            {
-                if (tma)
-                {
-                    // No proxy fence: this warp's reads of the stage (step s-1) have returned -- their values were
-                    // consumed before the __syncwarp that ended that step -- so the bulk copy cannot overtake them.
-                    if constexpr ((dbg & 16) != 0) fence_proxy_async();
-                    mbar_expect_tx_a(bar, ITEM_BYTES);
-                    tma_load_a(dst, ip, ITEM_BYTES, bar);
-                }
-                else mbar_arrive_a(bar);
-            }
-            return !tma;
-        };
-        // factors of one step -> ring slot ms as five compact column-major 4x4 blocks.  By TMA when the layout
-        // allows (one copy per item, per factor or per column), else element-wise.  Returns true for element-wise.
-        auto stage_facs = [&](bool live, int ms, const T *ap) -> bool {
-            if (!live) return false;
-            const unsigned dst = a_ms + ms * (MSTR * S);
-            const unsigned bar = b_mfull + 8 * ms;
-            const T *ap0   = reinterpret_cast<const T *>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ap), 0));
-            const bool a16 = __all_sync(0xffffffffu, lane >= D || aligned16(ap));
-            bool elem      = false;
-            if (a16 && lda4)
-            {
-                const bool contig = __all_sync(0xffffffffu, lane >= D || ap == ap0 + lane * 16);
-                if (lane == 0)
-                {
-                    // the slot's last readers (this warp and its P2 warp, step s-3) are ordered before this point by
-                    // the e_empty mbarrier this thread waited on in step s-1
-                    if constexpr ((dbg & 16) != 0) fence_proxy_async();
-                    mbar_expect_tx_a(bar, D * FAC_BYTES);
-                    if (contig) tma_load_a(dst, ap0, D * FAC_BYTES, bar);
-                }
-                if (!contig)
-                {
-                    __syncwarp();
-                    if (lane < D) tma_load_a(dst + lane * FAC_BYTES, ap, FAC_BYTES, bar);
-                }
-            }
-            else if (a16 && lda16)
+            if (contig)
             {
                 if (lane == 0)
                 {
                     if constexpr ((dbg & 16) != 0) fence_proxy_async();
-                    mbar_expect_tx_a(bar, D * FAC_BYTES);
+                    mbar_expect_tx_a(bar, (vtma ? ITEM_BYTES : 0u) + D * FAC_BYTES);
+                    if (vtma) tma_load_a(dst, ip, ITEM_BYTES, bar);
+                    tma_load_a(fdst, ap0, D * FAC_BYTES, bar);
                 }
-                __syncwarp();
-                const T *apj = reinterpret_cast<const T *>(
-                    __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ap), (lane >> 2) % D));
-                if (lane < 4 * D) tma_load_a(dst + lane * COL_BYTES, apj + (long long)(lane & 3) * lda, COL_BYTES, bar);
             }
             else
             {
-                elem = true;
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
+                const bool a16   = __all_sync(0xffffffffu, lane >= D || aligned16(ap));
+                const bool ftma  = a16 && (lda4 || lda16);
+                if (lane == 0)
                 {
-                    const int e  = lane + 32 * i; // element e = factor e/16, column (e%16)/4, row e%4
-                    const T *apj = reinterpret_cast<const T *>(
-                        __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ap), (e >> 4) % D));
-                    if (e < D * 16) cp_async_elem_a<T>(dst + e * S, apj + (e & 3) + (long long)((e >> 2) & 3) * lda);
+                    const unsigned bytes = (vtma ? ITEM_BYTES : 0u) + (ftma ? D * FAC_BYTES : 0u);
+                    if (bytes) mbar_expect_tx_a(bar, bytes); else mbar_arrive_a(bar);
+                    if (vtma) tma_load_a(dst, ip, ITEM_BYTES, bar);
                 }
-                if (lane == 0) mbar_arrive_a(bar);
+                __syncwarp();
+                if (ftma && lda4) { if (lane < D) tma_load_a(fdst + lane * FAC_BYTES, ap, FAC_BYTES, bar); }
+                else if (ftma)
+                {
+                    const T *apj = reinterpret_cast<const T *>(
+                        __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ap), (lane >> 2) % D));
+                    if (lane < 4 * D) tma_load_a(fdst + lane * COL_BYTES, apj + (long long)(lane & 3) * lda, COL_BYTES, bar);
+                }
+                else
+                {
+                    elem = true;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+                    {
+                        const int e  = lane + 32 * i; // element e = factor e/16, column (e%16)/4, row e%4
+                        const T *apj = reinterpret_cast<const T *>(
+                            __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ap), (e >> 4) % D));
+                        if (e < D * 16) cp_async_elem_a<T>(fdst + e * S, apj + (e & 3) + (long long)((e >> 2) & 3) * lda);
+                    }
+                }
             }
             return elem;
         };
         auto l2_pull = [&](const T *ip) {
             if (lane == 0 && ip && aligned16(ip)) l2_prefetch_bulk(ip, ITEM_BYTES);
         };
+        auto ld_in  = [&](int s) -> const T * { return (s < cnt) ? pin[s] : nullptr; };
+        auto ld_ap  = [&](int s) -> const T * { return (s < cnt) ? pa[(long long)s * D] : nullptr; };
+        auto ld_ap0 = [&](int s) -> const T * { return (s < cnt) ? pa0[(long long)s * D] : nullptr; };
 
-        // prologue: vector of step 0, L2 pull of step 1, factors of steps 0 and 1
-        const T *ip_b = in_ptr(1), *ip_c = in_ptr(2);   // inside the loop: vectors of steps s+1 and s+2
-        const T *ap_c = fac_ptr(2);                     //                  factor pointers of step s+2
-        bool el_0 = stage_data(true, 0, in_ptr(0));     // element-wise copies in flight for step s ...
-        el_0 |= stage_facs(true, 0, fac_ptr(0));
-        bool el_1 = stage_facs(cnt > 1, 1, fac_ptr(1)); // ... and for step s+1
-        l2_pull(ip_b);
+        // prologue: step 0 is staged, step 1 pulled into L2; pointers of steps 1 and 2 are on their way
+        bool el_cur = stage_step(true, 0, ld_in(0), ld_ap(0), ld_ap0(0));
         cp_async_commit();
-        int ms = 0, ms2 = 2;            // factor ring slots of step s and of step s+2
-        unsigned mph = 0;               // phase parity of slot ms
+        const T *ip_b = ld_in(1), *ip_c = ld_in(2);          // inside the loop: vectors of steps s+1 and s+2
+        const T *ap_b = ld_ap(1), *ap0_b = ld_ap0(1);        //                  factor pointers of step s+1
+        l2_pull(ip_b);
 
         for (int s = 0; s < cnt; ++s)
         {
             const int st = s & 1;
-            const T *ip_d = in_ptr(s + 3);       // pointer pipeline: fetched now, used next step
-            const T *ap_d = fac_ptr(s + 3);
+            const T *ip_d  = ld_in(s + 3);       // pointer pipeline: fetched now, used in later steps
+            const T *ap_c  = ld_ap(s + 2);
+            const T *ap0_c = ld_ap0(s + 2);
 
-            // the stage and the factor slot written below were last read in step s-1 / s-3 by this warp and in
-            // step s-3 by its P2 warp, which ended before this warp passed e_empty in step s-1
-            bool el_2 = stage_facs(s + 2 < cnt, ms2, ap_c);
-            el_1 |= stage_data(s + 1 < cnt, st ^ 1, ip_b);
+            // stage st^1 was last read by this warp in step s-1
+            const bool el_nxt = stage_step(s + 1 < cnt, st ^ 1, ip_b, ap_b, ap0_b);
             cp_async_commit();
             l2_pull(ip_c);                       // step s+2; its pointer was fetched a step ago
-            if (el_0)
+            if (el_cur)
             {
-                // element-wise route (vectors or factors that TMA cannot take): wait for the copies of step s,
-                // which were committed at least one group ago
+                // element-wise route: the copies of step s were committed one group ago
                 asm volatile("cp.async.wait_group 1;" ::: "memory");
                 __syncwarp();
             }
             mbar_wait_a(b_full + 8 * st, (unsigned)(s >> 1) & 1u);
-            mbar_wait_a(b_mfull + 8 * ms, mph);
 
             using P = typename V2<T>::type;
             P x[16]; // x[h] = my two adjacent columns of row h = (i0, i1)
+            const T *stage = IN + st * STG;
             {
-                const T *src = IN + st * N + 2 * lane;
+                const T *src = stage + 2 * lane;
 #pragma unroll
                 for (int h = 0; h < 16; ++h) x[h] = *reinterpret_cast<const P *>(src + h * 64);
-                const T *Ms = MS + ms * MSTR;
                 T m1[16], m0[16];
-                lds16<T>(Ms + 1 * 16, m1);
-                lds16<T>(Ms + 0 * 16, m0);
+                lds16<T>(stage + N + 1 * 16, m1);
+                lds16<T>(stage + N + 0 * 16, m0);
                 if constexpr ((dbg & 8) == 0)
                 {
                     tile16_apply_cm2<T, 1>(x, m1);
@@ -322,18 +297,21 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
                 }
                 else x[0].x += m1[0] + m0[0];
             }
+            // the three fast factors travel to P2 with the rows: 48 values, 16 bytes per lane
+            constexpr int FV = 16 / (int)S, FL = 48 / FV; // values per lane, lanes taking part
+            [[maybe_unused]] float4 fw;
+            if (lane < FL) fw = *reinterpret_cast<const float4 *>(stage + N + 2 * 16 + lane * FV);
             const int eb = s & 1;
-            T *Eb        = E + eb * 16 * PITCH;
+            T *Eb        = E + eb * EBUF;
             mbar_wait_a(b_eempty + 8 * eb, (((unsigned)(s >> 1)) & 1u) ^ 1u); // first use passes on a fresh barrier
 #pragma unroll
             for (int h = 0; h < 16; ++h) *reinterpret_cast<P *>(Eb + h * PITCH + 2 * lane) = x[h];
+            if (lane < FL) *reinterpret_cast<float4 *>(Eb + 16 * PITCH + lane * FV) = fw;
             __syncwarp();
             if (lane == 0) mbar_arrive_a(b_efull + 8 * eb);
 
-            ip_b = ip_c; ip_c = ip_d; ap_c = ap_d;
-            el_0 = el_1; el_1 = el_2;
-            if (++ms == NMB) { ms = 0; mph ^= 1u; }
-            if (++ms2 == NMB) ms2 = 0;
+            ip_b = ip_c; ip_c = ip_d; ap_b = ap_c; ap0_b = ap0_c;
+            el_cur = el_nxt;
         }
     }
     else
@@ -347,18 +325,15 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
         T *const *pout = out + kq0;
         T *o_cur  = pout[0];
         T *o_next = (cnt > 1) ? pout[1] : nullptr; // output pointers are fetched two steps ahead
-        int ms = 0;
-        unsigned mph = 0;
 
         for (int s = 0; s < cnt; ++s)
         {
             T *o_next2   = (s + 2 < cnt) ? pout[s + 2] : nullptr;
             const int eb = s & 1;
-            T *Eb        = E + eb * 16 * PITCH;
+            T *Eb        = E + eb * EBUF;
             T *erow      = Eb + row * PITCH;
-            const T *Mq  = MS + ms * MSTR;
+            const T *Mq  = Eb + 16 * PITCH - 2 * 16; // factors 2, 3, 4 follow the rows (indexed Mq + j*16 below)
             mbar_wait_a(b_efull + 8 * eb, (unsigned)(s >> 1) & 1u);
-            mbar_wait_a(b_mfull + 8 * ms, mph); // complete long ago: makes the TMA writes visible here
             {
                 // f4[k] = (F4(2hf, k), F4(2hf+1, k)): my two rows of the fastest factor; f3: the second fastest
                 P f4[4];
@@ -455,7 +430,6 @@ kron_wspec5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
             if (lane == 0) mbar_arrive_a(b_eempty + 8 * eb); // every read of E and of this step's factors is done
             o_cur  = o_next;
             o_next = o_next2;
-            if (++ms == NMB) { ms = 0; mph ^= 1u; }
         }
     }
 }

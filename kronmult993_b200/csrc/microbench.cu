@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
+#include <string>
 #include <vector>
 
 #define CK(x)                                                                                           \
@@ -136,8 +137,65 @@ static float time_ms(F &&launch, int reps = 3)
     return best;
 }
 
-int main()
+// FMA issue rate of FEW warps: one CTA of `warps` warps per SM, ILP independent chains per thread.  Reports warp
+// instructions per clock per SM sub-partition (4 warps -> one per sub-partition); peak is 0.5 (DFMA) / 1.0 (FFMA).
+template<typename T, int ILP>
+__global__ void fma_few_kernel(T *out, int iters, T a, T b, long long *clk)
 {
+    T acc[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) acc[i] = T(threadIdx.x + i);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it)
+    {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) acc[i] = acc[i] * a + b;
+    }
+    const long long t1 = clock64();
+    T s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += acc[i];
+    if (s == T(-12345.678)) out[0] = s;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *clk = t1 - t0;
+}
+
+template<typename T, int ILP>
+static void few_warps(const char *name, int sms, double *sink)
+{
+    long long *d_clk, h_clk = 0;
+    CK(cudaMalloc(&d_clk, 8));
+    for (int warps : {1, 4, 8, 12, 16, 32})
+    {
+        const int iters = 1 << 13;
+        fma_few_kernel<T, ILP><<<sms, 32 * warps>>>((T *)sink, iters, (T)1.0000001, (T)1e-9, d_clk);
+        CK(cudaDeviceSynchronize());
+        fma_few_kernel<T, ILP><<<sms, 32 * warps>>>((T *)sink, iters, (T)1.0000001, (T)1e-9, d_clk);
+        CK(cudaMemcpy(&h_clk, d_clk, 8, cudaMemcpyDeviceToHost));
+        const double per_smsp = (double)iters * ILP * ((warps + 3) / 4) / (double)h_clk;
+        printf("{\"bench\": \"%s\", \"ilp\": %d, \"warps_per_sm\": %d, \"clk\": %lld, \"warp_inst_per_clk_per_smsp\": %.3f}\n",
+               name, ILP, warps, h_clk, per_smsp);
+    }
+    CK(cudaFree(d_clk));
+}
+
+int main(int argc, char **argv)
+{
+    if (argc > 1 && std::string(argv[1]) == "issue")
+    {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, 0));
+        double *sink;
+        CK(cudaMalloc(&sink, 1024));
+        few_warps<double, 1>("dfma_few", prop.multiProcessorCount, sink);
+        few_warps<double, 2>("dfma_few", prop.multiProcessorCount, sink);
+        few_warps<double, 4>("dfma_few", prop.multiProcessorCount, sink);
+        few_warps<double, 8>("dfma_few", prop.multiProcessorCount, sink);
+        few_warps<double, 16>("dfma_few", prop.multiProcessorCount, sink);
+        few_warps<float, 1>("ffma_few", prop.multiProcessorCount, sink);
+        few_warps<float, 4>("ffma_few", prop.multiProcessorCount, sink);
+        few_warps<float, 8>("ffma_few", prop.multiProcessorCount, sink);
+        return 0;
+    }
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
     const int sms = prop.multiProcessorCount;
