@@ -49,156 +49,189 @@ struct Dmma84
     static constexpr int THREADS = WARPS * 32;
     static constexpr int T1      = 64 / WARPS;      // phase-1 slices per warp
     static constexpr int P2      = 32 / WARPS;      // phase-2 slice pairs per warp
-    static constexpr int SMEM    = 2 * N * 8;       // double-buffered exchange
+    static constexpr int SMEM    = 2 * N * 8 + 32;  // two item slots + their mbarriers
 };
 
+// Items arrive by TMA: one elected thread fetches item k+1 with a single 32 KiB cp.async.bulk into the other slot
+// right after the barrier of item k (every warp has then left item k-1, the slot's last user), and pulls item k+3
+// into L2 with one cp.async.bulk.prefetch.L2.  Phase 1 reads its 512-byte slices from the slot and writes them
+// back swizzled IN PLACE (a slice is read and rewritten by the same warp), phase 2 reads slice pairs, the flush
+// reuses the slot.  One CTA barrier per item (two when a run ends).  ncu on the previous version, which loaded
+// phase 1 straight from global memory, showed 7-12 long-scoreboard stall cycles per issued instruction.
 __global__ void __launch_bounds__(Dmma84::THREADS, 3)
 kron_dmma84_kernel(const double *const *__restrict__ A, double *const *__restrict__ in, double *const *__restrict__ out,
-                   const int lda, const int nb, const int chunk)
+                   const int lda, const int nb, const long long items_per_cta)
 {
     using C = Dmma84;
     constexpr int N = C::N, T1 = C::T1, P2 = C::P2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *E = reinterpret_cast<double *>(smem_raw); // [2][4096]
+    double *E     = reinterpret_cast<double *>(smem_raw); // [2][4096]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(E + 2 * N);
 
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
     const int g = lane >> 2, q = lane & 3;
+
+    const long long k0 = (long long)blockIdx.x * items_per_cta;
+    long long kend     = k0 + items_per_cta;
+    if (kend > nb) kend = nb;
+    if (k0 >= kend) return;
+
+    if (t == 0)
+    {
+        mbar_init(bar + 0, 1);
+        mbar_init(bar + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
     double acc[P2][4];
 #pragma unroll
     for (int j = 0; j < P2; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
 
-    const long long ngroups = (nb + (long long)chunk - 1) / chunk;
-    for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x)
-    {
-        const long long k0   = grp * chunk;
-        const long long kend = (k0 + chunk < nb) ? k0 + chunk : nb;
-
-        // software pipeline over items: factor fragments one item ahead, their pointers two ahead
-        const int lane_off0 = g + (2 * q) * lda; // M[g][2q]; M[g][2q+1] is lda further
-        const double *ap[4];
-        double a_nxt[8];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
+    // item k -> slot (k - k0) & 1, thread 0 only; vectors that are not 16-byte aligned are read from global memory
+    auto issue = [&](long long k, const double *ip) {
+        uint64_t *b = bar + ((k - k0) & 1);
+        if (aligned16(ip))
         {
-            const double *p0 = A[k0 * 4 + j];
-            a_nxt[2 * j]     = __ldg(p0 + lane_off0);
-            a_nxt[2 * j + 1] = __ldg(p0 + lane_off0 + lda);
-            ap[j]            = (k0 + 1 < kend) ? A[(k0 + 1) * 4 + j] : nullptr;
+            fence_proxy_async(); // the slot was last WRITTEN through the generic proxy (in-place phase 1, flush)
+            mbar_arrive_expect_tx(b, N * 8);
+            tma_load_1d(E + ((k - k0) & 1) * N, ip, N * 8, b);
         }
-        // L2 prefetch of the first two items (256 lines of 128 B per item, 2 per thread)
-#pragma unroll
-        for (int a = 0; a < 2; ++a)
-            if (k0 + a < kend)
-            {
-                const double *ip = in[k0 + a];
-                prefetch_l2(ip + t * 16);
-                prefetch_l2(ip + (t + 128) * 16);
-            }
-        double *o_cur = out[k0];
-        __syncthreads(); // previous group's phase-2 readers are done with both exchange buffers
+        else mbar_arrive(b);
+    };
+    auto l2_pull = [&](const double *ip) {
+        if (aligned16(ip)) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ip), "r"(N * 8) : "memory");
+    };
 
-        for (long long k = k0; k < kend; ++k)
+    // software pipeline over items: factor fragments one item ahead, their pointers two ahead
+    const int lane_off0 = g + (2 * q) * lda; // M[g][2q]; M[g][2q+1] is lda further
+    const double *ap[4];
+    double a_nxt[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+    {
+        const double *p0 = A[k0 * 4 + j];
+        a_nxt[2 * j]     = __ldg(p0 + lane_off0);
+        a_nxt[2 * j + 1] = __ldg(p0 + lane_off0 + lda);
+        ap[j]            = (k0 + 1 < kend) ? A[(k0 + 1) * 4 + j] : nullptr;
+    }
+    const double *ip_cur = in[k0];
+    const double *ip_nxt = (k0 + 1 < kend) ? in[k0 + 1] : nullptr;
+    if (t == 0)
+    {
+        issue(k0, ip_cur);
+        if (ip_nxt) l2_pull(ip_nxt);
+        if (k0 + 2 < kend) l2_pull(in[k0 + 2]);
+    }
+    double *o_cur = out[k0];
+
+    for (long long k = k0; k < kend; ++k)
+    {
+        const int cur = (int)((k - k0) & 1);
+        double *Ec    = E + cur * N;
+        double a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = a_nxt[i];
+        const double *ip_n2 = nullptr;
+        if (k + 1 < kend)
         {
-            const int cur = (int)((k - k0) & 1);
-            double *Ec    = E + cur * N;
-            double a[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = a_nxt[i];
-            if (k + 1 < kend)
+            for (int j = 0; j < 4; ++j)
+            {
+                a_nxt[2 * j]     = __ldg(ap[j] + lane_off0);
+                a_nxt[2 * j + 1] = __ldg(ap[j] + lane_off0 + lda);
+            }
+            if (k + 2 < kend)
             {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                {
-                    a_nxt[2 * j]     = __ldg(ap[j] + lane_off0);
-                    a_nxt[2 * j + 1] = __ldg(ap[j] + lane_off0 + lda);
-                }
-                if (k + 2 < kend)
-                {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) ap[j] = A[(k + 2) * 4 + j];
-                    const double *ip2 = in[k + 2];
-                    prefetch_l2(ip2 + t * 16);
-                    prefetch_l2(ip2 + (t + 128) * 16);
-                }
+                for (int j = 0; j < 4; ++j) ap[j] = A[(k + 2) * 4 + j];
+                ip_n2 = in[k + 2];
             }
+        }
 
-            // ---------------- phase 1: factors 3 (index i3 = u) and 2 (index i2 = v), from global
-            const double *__restrict__ ip = in[k];
-            const bool vec = aligned16(ip);
+        // ---------------- phase 1: factors 3 (index i3 = u) and 2 (index i2 = v), slice by slice, in place
+        const bool vec = aligned16(ip_cur);
+        mbar_wait(bar + cur, (unsigned)((k - k0) >> 1) & 1u);
 #pragma unroll
-            for (int tt = 0; tt < T1; ++tt)
+        for (int tt = 0; tt < T1; ++tt)
+        {
+            const int h = w * T1 + tt;
+            double x0, x1;
+            if (vec)
             {
-                const int h       = w * T1 + tt;
-                const double *src = ip + h * 64 + g * 8 + 2 * q;
-                double x0, x1;
-                if (vec)
-                {
-                    const double2 v = __ldg(reinterpret_cast<const double2 *>(src));
-                    x0 = v.x; x1 = v.y;
-                }
-                else { x0 = __ldg(src); x1 = __ldg(src + 1); }
-                double y0, y1, z0, z1;
-                dmma884(y0, y1, a[6], x0, 0.0, 0.0);
-                dmma884(y0, y1, a[7], x1, y0, y1);
-                dmma884(z0, z1, a[4], y0, 0.0, 0.0);
-                dmma884(z0, z1, a[5], y1, z0, z1);
-                const int chunk16 = (4 * g + q) ^ dmma_sigma(h);
-                *reinterpret_cast<double2 *>(Ec + h * 64 + chunk16 * 2) = make_double2(z0, z1);
+                const double2 v = *reinterpret_cast<const double2 *>(Ec + h * 64 + g * 8 + 2 * q);
+                x0 = v.x; x1 = v.y;
             }
-            __syncthreads();
+            else { x0 = __ldg(ip_cur + h * 64 + g * 8 + 2 * q); x1 = __ldg(ip_cur + h * 64 + g * 8 + 2 * q + 1); }
+            double y0, y1, z0, z1;
+            dmma884(y0, y1, a[6], x0, 0.0, 0.0);
+            dmma884(y0, y1, a[7], x1, y0, y1);
+            dmma884(z0, z1, a[4], y0, 0.0, 0.0);
+            dmma884(z0, z1, a[5], y1, z0, z1);
+            __syncwarp(); // every lane has read its chunk of the slice before the slice is rewritten
+            const int chunk16 = (4 * g + q) ^ dmma_sigma(h);
+            *reinterpret_cast<double2 *>(Ec + h * 64 + chunk16 * 2) = make_double2(z0, z1);
+        }
+        __syncthreads();
+        // every warp has left item k-1 (phase 2 and flush read the other slot): refill it
+        if (t == 0)
+        {
+            if (ip_nxt) issue(k + 1, ip_nxt);
+            if (k + 3 < kend) l2_pull(in[k + 3]);
+        }
 
-            // ---------------- phase 2: factors 1 (index i1 = u) and 0 (index i0 = v), slice pairs
+        // ---------------- phase 2: factors 1 (index i1 = u) and 0 (index i0 = v), slice pairs
+#pragma unroll
+        for (int jj = 0; jj < P2; ++jj)
+        {
+            const int j   = w * P2 + jj; // slices f = 2j, 2j+1
+            const int h0  = g * 8 + 2 * q;
+            const int sg  = ((g & 1) << 2) | q; // dmma_sigma(h0) == dmma_sigma(h0+1)
+            const double2 v0 = *reinterpret_cast<const double2 *>(Ec + h0 * 64 + ((j ^ sg) << 1));
+            const double2 v1 = *reinterpret_cast<const double2 *>(Ec + (h0 + 1) * 64 + ((j ^ sg) << 1));
+            double y0, y1;
+            dmma884(y0, y1, a[2], v0.x, 0.0, 0.0);
+            dmma884(y0, y1, a[3], v1.x, y0, y1);
+            dmma884(acc[jj][0], acc[jj][1], a[0], y0, acc[jj][0], acc[jj][1]);
+            dmma884(acc[jj][0], acc[jj][1], a[1], y1, acc[jj][0], acc[jj][1]);
+            dmma884(y0, y1, a[2], v0.y, 0.0, 0.0);
+            dmma884(y0, y1, a[3], v1.y, y0, y1);
+            dmma884(acc[jj][2], acc[jj][3], a[0], y0, acc[jj][2], acc[jj][3]);
+            dmma884(acc[jj][2], acc[jj][3], a[1], y1, acc[jj][2], acc[jj][3]);
+        }
+
+        double *o_next = (k + 1 < kend) ? out[k + 1] : nullptr;
+        if (o_next != o_cur) // uniform over the CTA
+        {
+            // A lane's sums sit at Out[i0 = g][i1 = 2q + s][f = 2j + t] (acc[jj][s + 2t]): addresses
+            // 512 B apart across lanes.  128-byte-strided REDs are ~7x slower than coalesced ones
+            // (profiles/microbench_r01.jsonl), so transpose through the slot first: each warp overwrites
+            // exactly the elements it alone read in phase 2 (no barrier needed before), then the CTA
+            // reads the item linearly and issues sector-complete REDs.
 #pragma unroll
             for (int jj = 0; jj < P2; ++jj)
             {
-                const int j   = w * P2 + jj; // slices f = 2j, 2j+1
-                const int h0  = g * 8 + 2 * q;
-                const int sg  = ((g & 1) << 2) | q; // dmma_sigma(h0) == dmma_sigma(h0+1)
-                const double2 v0 = *reinterpret_cast<const double2 *>(Ec + h0 * 64 + ((j ^ sg) << 1));
-                const double2 v1 = *reinterpret_cast<const double2 *>(Ec + (h0 + 1) * 64 + ((j ^ sg) << 1));
-                double y0, y1;
-                dmma884(y0, y1, a[2], v0.x, 0.0, 0.0);
-                dmma884(y0, y1, a[3], v1.x, y0, y1);
-                dmma884(acc[jj][0], acc[jj][1], a[0], y0, acc[jj][0], acc[jj][1]);
-                dmma884(acc[jj][0], acc[jj][1], a[1], y1, acc[jj][0], acc[jj][1]);
-                dmma884(y0, y1, a[2], v0.y, 0.0, 0.0);
-                dmma884(y0, y1, a[3], v1.y, y0, y1);
-                dmma884(acc[jj][2], acc[jj][3], a[0], y0, acc[jj][2], acc[jj][3]);
-                dmma884(acc[jj][2], acc[jj][3], a[1], y1, acc[jj][2], acc[jj][3]);
+                const int j  = w * P2 + jj;
+                const int h0 = g * 8 + 2 * q;
+                const int sg = ((g & 1) << 2) | q;
+                *reinterpret_cast<double2 *>(Ec + h0 * 64 + ((j ^ sg) << 1))       = make_double2(acc[jj][0], acc[jj][2]);
+                *reinterpret_cast<double2 *>(Ec + (h0 + 1) * 64 + ((j ^ sg) << 1)) = make_double2(acc[jj][1], acc[jj][3]);
+                acc[jj][0] = acc[jj][1] = acc[jj][2] = acc[jj][3] = 0.0;
             }
-
-            double *o_next = (k + 1 < kend) ? out[k + 1] : nullptr;
-            if (o_next != o_cur) // uniform over the CTA
-            {
-                // A lane's sums sit at Out[i0 = g][i1 = 2q + s][f = 2j + t] (acc[jj][s + 2t]): addresses
-                // 512 B apart across lanes.  128-byte-strided REDs are ~7x slower than coalesced ones
-                // (profiles/microbench_r01.jsonl), so transpose through the exchange buffer first: each
-                // warp overwrites exactly the elements it alone read in phase 2 (no barrier needed
-                // before), then the CTA reads the item linearly and issues sector-complete REDs.
-#pragma unroll
-                for (int jj = 0; jj < P2; ++jj)
-                {
-                    const int j  = w * P2 + jj;
-                    const int h0 = g * 8 + 2 * q;
-                    const int sg = ((g & 1) << 2) | q;
-                    *reinterpret_cast<double2 *>(Ec + h0 * 64 + ((j ^ sg) << 1))       = make_double2(acc[jj][0], acc[jj][2]);
-                    *reinterpret_cast<double2 *>(Ec + (h0 + 1) * 64 + ((j ^ sg) << 1)) = make_double2(acc[jj][1], acc[jj][3]);
-                    acc[jj][0] = acc[jj][1] = acc[jj][2] = acc[jj][3] = 0.0;
-                }
-                __syncthreads();
+            __syncthreads();
 #pragma unroll 4
-                for (int i = 0; i < N / 2 / C::THREADS; ++i)
-                {
-                    const int c  = t + i * C::THREADS; // 16-byte chunk of the item, linear order
-                    const int h  = c >> 5;
-                    const double2 v = *reinterpret_cast<const double2 *>(Ec + h * 64 + (((c & 31) ^ dmma_sigma(h)) << 1));
-                    red_add(o_cur + 2 * c, v.x);
-                    red_add(o_cur + 2 * c + 1, v.y);
-                }
+            for (int i = 0; i < N / 2 / C::THREADS; ++i)
+            {
+                const int c  = t + i * C::THREADS; // 16-byte chunk of the item, linear order
+                const int h  = c >> 5;
+                const double2 v = *reinterpret_cast<const double2 *>(Ec + h * 64 + (((c & 31) ^ dmma_sigma(h)) << 1));
+                red_add(o_cur + 2 * c, v.x);
+                red_add(o_cur + 2 * c + 1, v.y);
             }
-            o_cur = o_next;
         }
+        o_cur  = o_next;
+        ip_cur = ip_nxt;
+        ip_nxt = ip_n2;
     }
 }
 
@@ -213,13 +246,12 @@ static cudaError_t launch_dmma84(int sms, const double *const *A, int lda, doubl
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    long long chunk = nb / ((long long)sms * 3 * 8);
-    if (chunk < 1) chunk = 1;
-    if (chunk > 64) chunk = 64;
-    const long long ngroups  = (nb + chunk - 1) / chunk;
-    const long long max_grid = (long long)sms * 3;
-    const int grid           = (int)(ngroups < max_grid ? ngroups : max_grid);
-    kron_dmma84_kernel<<<grid, C::THREADS, C::SMEM, st>>>(A, in, out, lda, nb, (int)chunk);
+    // one contiguous range of items per CTA (runs of equal output pointers stay together), one wave of CTAs
+    long long grid = (long long)sms * 3;
+    long long ipc  = ((long long)nb + grid - 1) / grid;
+    if (ipc > 64) ipc = (ipc + 31) / 32 * 32;
+    grid = ((long long)nb + ipc - 1) / ipc;
+    kron_dmma84_kernel<<<(int)grid, C::THREADS, C::SMEM, st>>>(A, in, out, lda, nb, ipc);
     launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
