@@ -92,7 +92,10 @@ const char *kronmult_b200_last_path(void);
  * Unsupported combinations make the next call return cudaErrorInvalidValue.  For tests. */
 int kronmult_b200_force_path(int path);
 /* knobs.  0: regtile operand staging (0 = TMA into shared memory, 1 = L1 prefetch; development).
- *         1: implicit planning in the blocking entry points (1 = on, default; 0 = off). */
+ *         1: implicit planning in the blocking entry points (1 = on, default; 0 = off).
+ *         2: ablation variants of the n=4, d=5 kernel (only in builds with -DKRON_WSPEC5_EXPERIMENTS).
+ *         3: largest vector, in KiB, that the shape-agnostic path keeps resident in shared memory in one pass
+ *            (default 56); longer vectors take the tiled multi-pass route, which works in place in `in`. */
 int kronmult_b200_set_tuning(int knob, int value);
 
 #ifdef __cplusplus

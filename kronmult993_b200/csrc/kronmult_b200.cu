@@ -25,6 +25,7 @@ namespace kron
 
 static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_force{PATH_AUTO};
+static std::atomic<int> g_generic_resident_kib{56}; // knob 3: largest vector (KiB) the generic path keeps resident
 static thread_local const char *t_last_path = "none";
 
 struct DeviceInfo
@@ -134,7 +135,10 @@ static cudaError_t plan_generic(GenericPlan<T> &plan, const DeviceInfo &di, int 
     base.d = d; base.n = n; base.lda = lda; base.nb = nb;
 
     const int resident_budget = 96 * 1024;           // two CTAs per SM when the accumulator fits
-    const long long resident_max = (long long)(di.smem_optin - 4096) / s;
+    // One resident pass only while two CTAs (tile + run accumulator each) share an SM: the loads of one overlap
+    // the products of the other.  A vector that fills the SM alone (1 CTA, synchronous loads) measured 1.7-2.6x
+    // slower than the tiled multi-pass route below (n = 5, d = 6 and n = 6, d = 5 on B200).
+    const long long resident_max = (long long)g_generic_resident_kib.load(std::memory_order_relaxed) * 1024 / s;
     if (fast_done == 0 && (d == 0 || N <= resident_max))
     {
         PassParams<T> p = base;
@@ -428,6 +432,7 @@ int kronmult_b200_set_tuning(int knob, int value)
     if (knob == 0) { kron::g_regtile_stage.store(value); return 0; }
     if (knob == 1) { kron::g_autoplan.store(value); return 0; }
     if (knob == 2) { kron::g_wspec5_dbg.store(value); return 0; }
+    if (knob == 3 && value >= 1 && value <= 220) { kron::g_generic_resident_kib.store(value); return 0; }
     return (int)cudaErrorInvalidValue;
 }
 int kronmult_b200_force_path(int path)

@@ -225,6 +225,7 @@ def test_explicit_plan_on_shuffled_batches(kron, oracle_mod, n, d, nb, r, dt):
     assert oracle_mod.rel_l2(p.out_slab.cpu().numpy(), exp) <= _tol(hp)
     # the data may change between executions of the same plan: run again on new inputs (outputs keep accumulating)
     p.in_slab.mul_(-2.0)
+    s.wait_stream(torch.cuda.current_stream())  # the update above runs on torch's current stream
     plan.execute(s)
     s.synchronize()
     got2 = p.out_slab.cpu().numpy()
