@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libkronmult_b200.so")
 MICROBENCH = os.path.join(_HERE, "kron_microbench")
+OBJ = os.path.join(_HERE, "_obj")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "--std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", *ARCH]
@@ -47,10 +48,19 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         return LIB
     units = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))
              if f.endswith((".cu", ".cpp")) and not f.startswith("microbench")]
-    cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", LIB, *units, "-lpthread"]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    subprocess.run(cmd, check=True, cwd=CSRC)
+    # one nvcc process per translation unit, all at once (the pairtile instantiations dominate), then link
+    os.makedirs(OBJ, exist_ok=True)
+    procs = []
+    for u in units:
+        o = os.path.join(OBJ, os.path.splitext(os.path.basename(u))[0] + ".o")
+        cmd = [_nvcc(), *NVCC_FLAGS, "-c", u, "-o", o]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((o, cmd, subprocess.Popen(cmd, cwd=CSRC)))
+    for o, cmd, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
+    subprocess.run([_nvcc(), *ARCH, "-shared", "-o", LIB, *[o for o, _, _ in procs], "-lpthread"], check=True, cwd=CSRC)
     return LIB
 
 

@@ -16,7 +16,8 @@ enum Path : int
     PATH_DMMA    = 4, // n = 8 on the FP64 tensor pipe (mma.sync m8n8k4), double only
     PATH_WSPEC   = 5, // n = 4, d = 5,6: warp-specialised two-phase kernel with 64-value register tiles
     PATH_WSPEC5  = 6, // n = 4, d = 5: two items per step, split rows, double-buffered exchange
-    PATH_LAST    = PATH_WSPEC5,
+    PATH_PAIRTILE = 7, // compile-time (n, d), n x n register tiles, two factors per shared-memory round trip
+    PATH_LAST    = PATH_PAIRTILE,
 };
 
 __host__ __device__ constexpr int ipow(int b, int e)

@@ -1,0 +1,486 @@
+// kernel_pairtile.cuh -- compile-time (n, d) kernels built from n x n register tiles ("pairtile" path).
+//
+// Replaces cuda_kronmult_batchelement / cuda_kronmult / transpose / multiply_transpose
+// (kronmult_gpu/kronmult.cu:139-167, :95-130, :34-43, :54-78) for the shapes of the reference's sweep
+// envelope (tests/kronmult_fullbench_gpu.cpp:70-74, n in [2,10], d in [2,6]) whose vector fits in shared
+// memory and that no more specialised family (tiny, dmma, wspec, wspec5, regtile) claims.
+//
+// Design (not a port):
+//  * The item's vector lives in shared memory; the d mode products are applied in place, TWO factors per
+//    round trip: a thread owns an n x n tile (the two indices of a factor pair), pulls it into registers,
+//    applies the faster factor along the rows and the slower one along the columns (2 n^3 FMAs per
+//    2 n^2 shared-memory accesses) and writes it back.  Odd d ends with a single-factor pass on the
+//    same tile shape.  Every dot product sums k ascending from 0 like multiply_transpose
+//    (kronmult.cu:66-70).  The reference moves 2 n^d elements through GLOBAL memory per factor.
+//  * Layout: logical index i sits at i + PADE * (i / n^2): for even n the n^2-element blocks are padded
+//    by 16 bytes so that their pitch is an odd number of 16-byte units -- the first pass, where every
+//    lane owns one contiguous block, then runs on conflict-free 128-bit accesses; odd n needs no pad
+//    (odd pitch, scalar accesses).  Later passes walk consecutive lanes along the fastest free index.
+//  * B items ("streams") side by side per CTA when n^(d-2) tiles do not fill it; every stream walks a
+//    range of consecutive items, so runs of equal output pointers are summed on chip (accumulator in
+//    shared memory, touched by the same thread every time -> no synchronisation) and flushed once.
+//    Every flush is REDG, like the reference's atomicAdd (kronmult.cu:126-129).
+//  * Two stages: vector and factors of the next step arrive by cp.async (16-byte chunks when the
+//    item is 16-byte aligned, element-wise otherwise; factors element-wise and transposed on the fly to
+//    row-major with an even pitch, so rows are fetched as broadcast 128-bit loads), pointers one
+//    step further ahead.  Vectors too large for two stages plus the accumulator use one stage.
+#pragma once
+#include "common.cuh"
+#include "kernel_regtile.cuh" // cp_async_elem / cp_async_commit / cp_async_wait_all
+#include <atomic>
+
+namespace kron
+{
+
+template<typename T, int n, int d>
+struct PairCfg
+{
+    static constexpr int S     = (int)sizeof(T);
+    static constexpr int N     = ipow(n, d);
+    static constexpr int NSQ   = n * n;
+    static constexpr int TP    = N / NSQ; // tiles (= columns of every pass) per item
+    static constexpr int VEC   = 16 / S;
+    static constexpr bool VECTILE = (NSQ % VEC) == 0;
+    static constexpr int PADE  = (VECTILE && ((NSQ / VEC) % 2) == 0) ? VEC : 0;
+    static constexpr int BLK   = NSQ + PADE;
+    static constexpr int ITEM  = TP * BLK;
+    static constexpr int ITEMP = (ITEM + VEC - 1) / VEC * VEC; // item pitch: 16-byte multiple
+    static constexpr int RP    = (n + VEC - 1) / VEC * VEC;    // factor row pitch
+    static constexpr int MAT   = d * n * RP;
+    static constexpr int NPAIR = d / 2;
+    static constexpr int ODD   = d % 2;
+    static constexpr int NPASS = NPAIR + ODD;
+    static constexpr int NCH   = N / VEC; // whole 16-byte chunks of a vector
+    static constexpr int TAIL  = N % VEC;
+
+    // two CTAs per SM for the small tiles, one fat CTA otherwise
+    static constexpr int MINB   = (NSQ * S <= 128) ? 2 : 1;
+    static constexpr int BUDGET = (MINB == 2 ? 100 : 200) * 1024;
+    static constexpr int LIMIT  = 220 * 1024;
+    static constexpr int PTRB   = 3 * ((d + 2) * 8 + 4); // three slots of pointers + flag per stream
+
+    static constexpr int bytes_item(int stages, int acc) { return (stages + acc) * ITEMP * S + stages * MAT * S + PTRB; }
+    static constexpr int STAGES = bytes_item(2, 1) <= BUDGET ? 2 : 1;
+    static constexpr int ACC    = STAGES == 2 ? 1 : (bytes_item(1, 1) + 64 <= LIMIT ? 1 : 0);
+    static constexpr bool FITS  = bytes_item(STAGES, ACC) + 64 <= LIMIT;
+
+    static constexpr int bmax() { int b = BUDGET / bytes_item(STAGES, ACC); return b < 1 ? 1 : b; }
+    static constexpr int bwant() { int b = 256 / TP; return b < 1 ? 1 : b; }
+    static constexpr int B      = bwant() < bmax() ? bwant() : bmax();
+    static constexpr int TILES  = B * TP;
+    static constexpr int ITERS  = (TILES + 255) / 256;
+    static constexpr int THREADS = ((TILES + ITERS - 1) / ITERS + 31) / 32 * 32;
+
+    // byte offsets into dynamic shared memory
+    static constexpr int OFF_ACC  = STAGES * B * ITEMP * S;
+    static constexpr int OFF_MAT  = OFF_ACC + ACC * B * ITEMP * S;
+    static constexpr int OFF_PTR  = OFF_MAT + STAGES * B * MAT * S; // MAT*S is a 16-byte multiple (RP)
+    static constexpr int OFF_FLAG = OFF_PTR + 3 * B * (d + 2) * 8;
+    static constexpr int SMEM     = OFF_FLAG + ((3 * B * 4 + 15) / 16) * 16;
+};
+
+template<typename T, int n, int d, int PASS>
+struct PairGeom
+{
+    using C = PairCfg<T, n, d>;
+    static constexpr bool SINGLE = (PASS == C::NPAIR); // the trailing single-factor pass of an odd d
+    static constexpr bool FINAL  = (PASS == C::NPASS - 1);
+    static constexpr int sB_log  = SINGLE ? ipow(n, d - 2) : ipow(n, 2 * PASS);
+    static constexpr int sA_log  = sB_log * n;
+    static constexpr int LO      = sB_log; // columns below the tile's two indices
+    static constexpr int sH_log  = sA_log * n;
+    static constexpr int phys_stride(int x) { return x >= C::NSQ ? x / C::NSQ * C::BLK : x; }
+    static constexpr int sB_ph = phys_stride(sB_log);
+    static constexpr int sA_ph = phys_stride(sA_log);
+    static constexpr int sH_ph = phys_stride(sH_log);
+    static constexpr int jb    = d - 1 - 2 * PASS; // faster factor of the pair (unused when SINGLE)
+    static constexpr int ja    = SINGLE ? 0 : d - 2 - 2 * PASS;
+};
+
+// one row of a factor (row-major, pitch RP) as broadcast 128-bit loads
+template<typename T, int n, int RP>
+__device__ __forceinline__ void load_row(const T *__restrict__ row, T (&m)[n])
+{
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const int4 *q = reinterpret_cast<const int4 *>(row);
+#pragma unroll
+    for (int i = 0; i < RP / VEC; ++i)
+    {
+        const int4 w = q[i];
+        if constexpr (sizeof(T) == 8)
+        {
+            if (2 * i < n) m[2 * i] = __hiloint2double(w.y, w.x);
+            if (2 * i + 1 < n) m[2 * i + 1] = __hiloint2double(w.w, w.z);
+        }
+        else
+        {
+            if (4 * i < n) m[4 * i] = __int_as_float(w.x);
+            if (4 * i + 1 < n) m[4 * i + 1] = __int_as_float(w.y);
+            if (4 * i + 2 < n) m[4 * i + 2] = __int_as_float(w.z);
+            if (4 * i + 3 < n) m[4 * i + 3] = __int_as_float(w.w);
+        }
+    }
+}
+
+// One tile of one pass.  `vec` = the item's vector in shared memory, `acc` = the item's run accumulator,
+// `mats` = the item's d factors, `c` = column index in [0, TP), flag bits: 2 = first item of a run of
+// equal output pointers, 4 = last item of the run.
+template<typename T, int n, int d, int PASS>
+__device__ __forceinline__ void pair_tile(T *__restrict__ vec, T *__restrict__ acc, const T *__restrict__ mats,
+                                          int c, int flag, T *__restrict__ outp)
+{
+    using C = PairCfg<T, n, d>;
+    using G = PairGeom<T, n, d, PASS>;
+    constexpr bool REGFLUSH = G::FINAL && d >= 3; // results leave through REDG straight from registers
+
+    const int lo = (G::LO > 1) ? c % G::LO : 0;
+    const int hi = (G::LO > 1) ? c / G::LO : c;
+    int base_ph  = hi * G::sH_ph + lo;
+    if constexpr (C::PADE > 0 && G::LO > C::NSQ) base_ph += (lo / C::NSQ) * C::PADE;
+    const int base_log = hi * G::sH_log + lo;
+    T *__restrict__ x  = vec + base_ph;
+
+    T X[n][n];
+    if constexpr (PASS == 0 && !G::SINGLE && C::VECTILE)
+    {
+        const int4 *q = reinterpret_cast<const int4 *>(x);
+#pragma unroll
+        for (int i = 0; i < C::NSQ / C::VEC; ++i)
+        {
+            const int4 w = q[i];
+            if constexpr (sizeof(T) == 8)
+            {
+                X[(2 * i) / n][(2 * i) % n]         = __hiloint2double(w.y, w.x);
+                X[(2 * i + 1) / n][(2 * i + 1) % n] = __hiloint2double(w.w, w.z);
+            }
+            else
+            {
+                X[(4 * i) / n][(4 * i) % n]         = __int_as_float(w.x);
+                X[(4 * i + 1) / n][(4 * i + 1) % n] = __int_as_float(w.y);
+                X[(4 * i + 2) / n][(4 * i + 2) % n] = __int_as_float(w.z);
+                X[(4 * i + 3) / n][(4 * i + 3) % n] = __int_as_float(w.w);
+            }
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int a = 0; a < n; ++a)
+#pragma unroll
+            for (int b = 0; b < n; ++b) X[a][b] = x[a * G::sA_ph + b * G::sB_ph];
+    }
+
+    // faster factor along the rows: Z[a][b'] = sum_b Mb(b', b) X[a][b]
+    T Z[n][n];
+    if constexpr (!G::SINGLE)
+    {
+        const T *__restrict__ Mb = mats + G::jb * n * C::RP;
+#pragma unroll
+        for (int bp = 0; bp < n; ++bp)
+        {
+            T m[n];
+            load_row<T, n, C::RP>(Mb + bp * C::RP, m);
+#pragma unroll
+            for (int a = 0; a < n; ++a)
+            {
+                T dot = X[a][0] * m[0];
+#pragma unroll
+                for (int k = 1; k < n; ++k) dot += X[a][k] * m[k];
+                Z[a][bp] = dot;
+            }
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int a = 0; a < n; ++a)
+#pragma unroll
+            for (int b = 0; b < n; ++b) Z[a][b] = X[a][b];
+    }
+
+    // slower factor down the columns: Y[a'][b'] = sum_a Ma(a', a) Z[a][b']
+    const T *__restrict__ Ma = mats + G::ja * n * C::RP;
+#pragma unroll
+    for (int ap = 0; ap < n; ++ap)
+    {
+        T m[n];
+        load_row<T, n, C::RP>(Ma + ap * C::RP, m);
+        T y[n];
+#pragma unroll
+        for (int bp = 0; bp < n; ++bp)
+        {
+            T dot = Z[0][bp] * m[0];
+#pragma unroll
+            for (int k = 1; k < n; ++k) dot += Z[k][bp] * m[k];
+            y[bp] = dot;
+        }
+        if constexpr (REGFLUSH)
+        {
+#pragma unroll
+            for (int bp = 0; bp < n; ++bp)
+            {
+                const int ph = base_ph + ap * G::sA_ph + bp * G::sB_ph;
+                const int lg = base_log + ap * G::sA_log + bp * G::sB_log;
+                T v          = y[bp];
+                if constexpr (C::ACC)
+                {
+                    if (!(flag & 2)) v += acc[ph];
+                    if (flag & 4) red_add(outp + lg, v);
+                    else acc[ph] = v;
+                }
+                else { red_add(outp + lg, v); }
+            }
+        }
+        else if constexpr (PASS == 0 && !G::SINGLE && (n % 2) == 0)
+        {
+            // contiguous row of the tile: 2-element stores (n even keeps them aligned)
+#pragma unroll
+            for (int bp = 0; bp < n; bp += 2)
+            {
+                if constexpr (sizeof(T) == 8)
+                    *reinterpret_cast<double2 *>(x + ap * n + bp) = make_double2(y[bp], y[bp + 1]);
+                else
+                    *reinterpret_cast<float2 *>(x + ap * n + bp) = make_float2(y[bp], y[bp + 1]);
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int bp = 0; bp < n; ++bp) x[ap * G::sA_ph + bp * G::sB_ph] = y[bp];
+        }
+    }
+}
+
+template<typename T, int n, int d, int PASS>
+__device__ __forceinline__ void pair_passes(unsigned char *smem, int stage, const int *__restrict__ s_flag,
+                                            T *const *__restrict__ s_ptr)
+{
+    using C = PairCfg<T, n, d>;
+    T *vecs       = reinterpret_cast<T *>(smem) + (size_t)stage * C::B * C::ITEMP;
+    T *accs       = reinterpret_cast<T *>(smem + C::OFF_ACC);
+    const T *mats = reinterpret_cast<const T *>(smem + C::OFF_MAT) + (size_t)stage * C::B * C::MAT;
+#pragma unroll 1
+    for (int tl = threadIdx.x; tl < C::TILES; tl += C::THREADS)
+    {
+        const int b    = (C::B > 1) ? tl / C::TP : 0;
+        const int c    = (C::B > 1) ? tl - b * C::TP : tl;
+        const int flag = s_flag[b];
+        if (flag)
+            pair_tile<T, n, d, PASS>(vecs + b * C::ITEMP, accs + b * C::ITEMP, mats + b * C::MAT, c, flag,
+                                     s_ptr[b * (d + 2) + d + 1]);
+    }
+    if constexpr (PASS + 1 < C::NPASS)
+    {
+        __syncthreads();
+        pair_passes<T, n, d, PASS + 1>(smem, stage, s_flag, s_ptr);
+    }
+}
+
+template<typename T, int n, int d>
+__global__ void __launch_bounds__(PairCfg<T, n, d>::THREADS, PairCfg<T, n, d>::MINB)
+    kron_pairtile_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T *const *__restrict__ out,
+                         int lda, int nb)
+{
+    using C = PairCfg<T, n, d>;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x;
+
+    // this CTA's contiguous item range, cut into B streams of L consecutive items
+    const long long per = ((long long)nb + gridDim.x - 1) / gridDim.x;
+    const long long r0  = per * blockIdx.x;
+    long long r1        = r0 + per;
+    if (r1 > nb) r1 = nb;
+    if (r0 >= r1) return;
+    const int L = (int)((r1 - r0 + C::B - 1) / C::B);
+
+    auto slot_ptrs = [&](int slot) { return reinterpret_cast<T **>(smem + C::OFF_PTR) + (size_t)slot * C::B * (d + 2); };
+    auto slot_flag = [&](int slot) { return reinterpret_cast<int *>(smem + C::OFF_FLAG) + slot * C::B; };
+
+    // pointers of step t: per stream d factor pointers, input, output; flag = valid | first<<1 | last<<2
+    auto fetch_ptrs = [&](int t) {
+        T **sp  = slot_ptrs(t % 3);
+        int *sf = slot_flag(t % 3);
+        for (int e = tid; e < C::B * (d + 2); e += C::THREADS)
+        {
+            const int b        = e / (d + 2);
+            const int w        = e - b * (d + 2);
+            const long long s0 = r0 + (long long)b * L;
+            long long s1       = s0 + L;
+            if (s1 > r1) s1 = r1;
+            const long long k = s0 + t;
+            const bool valid  = k < s1;
+            T *p              = nullptr;
+            if (valid)
+            {
+                if (w < d) p = const_cast<T *>(A[k * d + w]);
+                else if (w == d) p = in[k];
+                else
+                {
+                    p                = out[k];
+                    const bool first = (t == 0) || (out[k - 1] != p);
+                    const bool last  = (k + 1 >= s1) || (out[k + 1] != p);
+                    sf[b]            = 1 | (first ? 2 : 0) | (last ? 4 : 0);
+                }
+            }
+            else if (w == d + 1) sf[b] = 0;
+            sp[e] = p;
+        }
+    };
+
+    // vector and factors of step t -> stage
+    auto issue_copies = [&](int t, int stage) {
+        T *const *sp  = slot_ptrs(t % 3);
+        const int *sf = slot_flag(t % 3);
+        T *vecs       = reinterpret_cast<T *>(smem) + (size_t)stage * C::B * C::ITEMP;
+        T *mats       = reinterpret_cast<T *>(smem + C::OFF_MAT) + (size_t)stage * C::B * C::MAT;
+        if constexpr (C::NCH > 0)
+        {
+            for (int e = tid; e < C::B * C::NCH; e += C::THREADS)
+            {
+                const int b = (C::B > 1) ? e / C::NCH : 0;
+                const int q = (C::B > 1) ? e - b * C::NCH : e;
+                if (!sf[b]) continue;
+                const T *src = sp[b * (d + 2) + d] + q * C::VEC;
+                int el       = q * C::VEC;
+                if constexpr (C::PADE > 0) el += (el / C::NSQ) * C::PADE;
+                T *dst = vecs + b * C::ITEMP + el;
+                if (aligned16(src))
+                {
+                    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dst);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
+                }
+                else
+                {
+#pragma unroll
+                    for (int i = 0; i < C::VEC; ++i) cp_async_elem<T>(dst + i, src + i);
+                }
+            }
+        }
+        if constexpr (C::TAIL > 0)
+        {
+            for (int e = tid; e < C::B * C::TAIL; e += C::THREADS)
+            {
+                const int b = e / C::TAIL;
+                const int i = C::NCH * C::VEC + (e - b * C::TAIL);
+                if (!sf[b]) continue;
+                cp_async_elem<T>(vecs + b * C::ITEMP + i, sp[b * (d + 2) + d] + i); // TAIL > 0 only without padding
+            }
+        }
+        for (int e = tid; e < C::B * d * C::NSQ; e += C::THREADS)
+        {
+            const int b  = e / (d * C::NSQ);
+            const int r  = e - b * (d * C::NSQ);
+            const int j  = r / C::NSQ;
+            const int rc = r - j * C::NSQ;
+            const int cc = rc / n;
+            const int rr = rc - cc * n;
+            if (!sf[b]) continue;
+            const T *Ap = sp[b * (d + 2) + j];
+            cp_async_elem<T>(mats + b * C::MAT + j * n * C::RP + rr * C::RP + cc, Ap + rr + (long long)cc * lda);
+        }
+        cp_async_commit();
+    };
+
+    fetch_ptrs(0);
+    __syncthreads();
+    issue_copies(0, 0);
+    if (L > 1) fetch_ptrs(1);
+
+    for (int t = 0; t < L; ++t)
+    {
+        const int stage = (C::STAGES == 2) ? (t & 1) : 0;
+        cp_async_wait_all();
+        __syncthreads(); // step t's data and step t+1's pointers are visible; the other stage is free
+        if constexpr (C::STAGES == 2)
+        {
+            if (t + 1 < L) issue_copies(t + 1, stage ^ 1);
+        }
+        if (t + 2 < L) fetch_ptrs(t + 2);
+
+        const int *sf = slot_flag(t % 3);
+        pair_passes<T, n, d, 0>(smem, stage, sf, slot_ptrs(t % 3));
+
+        if constexpr (d == 2)
+        {
+            // one thread per item in the pass above: leave through shared memory so that the REDG are coalesced
+            __syncthreads();
+            T *vecs = reinterpret_cast<T *>(smem) + (size_t)stage * C::B * C::ITEMP;
+            T *accs = reinterpret_cast<T *>(smem + C::OFF_ACC);
+            T *const *sp = slot_ptrs(t % 3);
+            for (int e = tid; e < C::B * C::N; e += C::THREADS)
+            {
+                const int b    = e / C::N;
+                const int i    = e - b * C::N;
+                const int flag = sf[b];
+                if (!flag) continue;
+                const int ph = b * C::ITEMP + i + (C::PADE > 0 ? (i / C::NSQ) * C::PADE : 0);
+                T v          = vecs[ph];
+                T *o         = sp[b * (d + 2) + d + 1] + i;
+                if constexpr (C::ACC)
+                {
+                    if (!(flag & 2)) v += accs[ph];
+                    if (flag & 4) red_add(o, v);
+                    else accs[ph] = v;
+                }
+                else { red_add(o, v); }
+            }
+        }
+        if constexpr (C::STAGES == 1)
+        {
+            if (t + 1 < L)
+            {
+                __syncthreads(); // the single stage is free again
+                issue_copies(t + 1, 0);
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+template<typename T, int n, int d>
+static cudaError_t launch_pairtile(int sms, const T *const *A, int lda, T *const *in, T *const *out, int nb,
+                                   cudaStream_t st, std::atomic<long long> &launches)
+{
+    using C = PairCfg<T, n, d>;
+    // fp64 tiles of n >= 9 do not fit the register file (2 n^2 live values)
+    if constexpr (!C::FITS || (sizeof(T) == 8 && n > 8)) { return cudaErrorNotSupported; }
+    else
+    {
+        auto kfn = kron_pairtile_kernel<T, n, d>;
+        if (C::SMEM > 48 * 1024)
+        {
+            cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+            if (e != cudaSuccess) return e;
+        }
+        const long long want = (long long)sms * C::MINB;
+        const int grid       = (int)(nb < want ? nb : want);
+        kfn<<<grid, C::THREADS, C::SMEM, st>>>(A, in, out, lda, nb);
+        launches.fetch_add(1, std::memory_order_relaxed);
+        return cudaGetLastError();
+    }
+}
+
+// cudaErrorNotSupported when (n, d) is outside the family; defined in pairtile_f64.cu / pairtile_f32.cu
+template<typename T>
+cudaError_t run_pairtile(int sms, int d, int n, const T *const *A, int lda, T *const *in, T *const *out, int nb,
+                         cudaStream_t st, std::atomic<long long> &launches);
+
+#define KRON_PAIRTILE_DEFINE(TYPE)                                                                                  \
+    template<>                                                                                                      \
+    cudaError_t run_pairtile<TYPE>(int sms, int d, int n, const TYPE *const *A, int lda, TYPE *const *in,           \
+                                   TYPE *const *out, int nb, cudaStream_t st, std::atomic<long long> &launches)    \
+    {                                                                                                               \
+        switch (n * 16 + d)                                                                                         \
+        {                                                                                                           \
+            KRON_PT_N(2) KRON_PT_N(3) KRON_PT_N(4) KRON_PT_N(5) KRON_PT_N(6) KRON_PT_N(7) KRON_PT_N(8) KRON_PT_N(9)   \
+            KRON_PT_N(10)                                                                                           \
+        default: return cudaErrorNotSupported;                                                                      \
+        }                                                                                                           \
+    }
+#define KRON_PT_CASE(NN, DD) \
+    case NN * 16 + DD: return launch_pairtile<KRON_PT_TYPE, NN, DD>(sms, A, lda, in, out, nb, st, launches);
+#define KRON_PT_N(NN) KRON_PT_CASE(NN, 2) KRON_PT_CASE(NN, 3) KRON_PT_CASE(NN, 4) KRON_PT_CASE(NN, 5) KRON_PT_CASE(NN, 6)
+
+} // namespace kron

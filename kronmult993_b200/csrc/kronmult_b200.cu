@@ -16,6 +16,7 @@
 #include "kernel_dmma.cuh"
 #include "kernel_wspec.cuh"
 #include "kernel_wspec5.cuh"
+#include "kernel_pairtile.cuh"
 
 #include <atomic>
 #include <mutex>
@@ -282,6 +283,12 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
         e = run_wspec5<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
         return e == cudaErrorNotSupported ? cudaErrorInvalidValue : e;
     }
+    if (force == PATH_PAIRTILE)
+    {
+        e = run_pairtile<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches);
+        if (e == cudaSuccess) t_last_path = "pairtile";
+        return e == cudaErrorNotSupported ? cudaErrorInvalidValue : e;
+    }
     if (force == PATH_DMMA)
     {
         int remaining = 0;
@@ -304,6 +311,9 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
     e = run_wspec<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
     if (e != cudaErrorNotSupported) return e;
     e = run_regtile<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
+    if (e != cudaErrorNotSupported) return e;
+    e = run_pairtile<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches);
+    if (e == cudaSuccess) t_last_path = "pairtile";
     if (e != cudaErrorNotSupported) return e;
     return run_generic<T>(di, d, n, A, lda, in, out, nb, st);
 }

@@ -280,3 +280,49 @@ def test_blocking_entry_plans_shuffled_batches_once(kron, oracle_mod):
         assert kron.plan_cache_counters() == (h3, b3)
     finally:
         kron.set_tuning(1, 1)
+
+
+def _pairtile_shapes(dt):
+    """(n, d) the pairtile family accepts: the vector (+ stage, + accumulator) fits in shared memory; fp64 tiles stop
+    at n = 8 (register file)."""
+    s = 8 if dt == torch.float64 else 4
+    out = []
+    for n in range(2, 11):
+        for d in range(2, 7):
+            if n ** d * s <= 140 * 1024 and not (s == 8 and n > 8):
+                out.append((n, d))
+    return out
+
+
+@pytest.mark.parametrize("n,d", _pairtile_shapes(torch.float64))
+def test_pairtile_fp64(kron, oracle_mod, n, d):
+    """Every compile-time (n, d) of the pairtile family, forced: ragged streams, runs of equal outputs that straddle
+    streams and CTAs, the reference's 5-output pattern with lda = 67, distinct outputs."""
+    N = n ** d
+    nb = max(7, min(1500, 400000 // N))
+    for alias, kw in (("runs", dict(items_per_output=5, lda=n + 1)), ("ref", dict(nb_distinct=5, matrices="reftest")),
+                      ("distinct", {})):
+        hp = batch.make_problem(d, n, nb, torch.float64, "cpu", seed=100 + n * 7 + d, alias=alias, **kw).to_host()
+        _check(kron, oracle_mod, hp, "pairtile")
+        assert kron.last_path() == "pairtile"
+
+
+@pytest.mark.parametrize("n,d", _pairtile_shapes(torch.float32))
+def test_pairtile_fp32(kron, oracle_mod, n, d):
+    N = n ** d
+    nb = max(7, min(1500, 400000 // N))
+    for alias, kw in (("runs", dict(items_per_output=5, lda=n + 1)), ("distinct", dict(matrices="reftest"))):
+        hp = batch.make_problem(d, n, nb, torch.float32, "cpu", seed=200 + n * 7 + d, alias=alias, **kw).to_host()
+        _check(kron, oracle_mod, hp, "pairtile")
+        assert kron.last_path() == "pairtile"
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("n,d,nb", [(4, 3, 1), (4, 3, 2), (4, 3, 149), (6, 4, 3), (6, 4, 1000), (5, 2, 1), (5, 2, 4097),
+                                    (3, 6, 297), (7, 3, 300), (2, 6, 5000)])
+def test_pairtile_ragged_and_misaligned(kron, oracle_mod, n, d, nb, dt):
+    """Batch sizes around the stream / CTA boundaries; vectors shifted by one element (element-wise cp.async route)."""
+    for mis in (0, 1):
+        hp = batch.make_problem(d, n, nb, dt, "cpu", seed=nb + mis, alias="runs", items_per_output=3, lda=n + 3,
+                                misalign=mis).to_host()
+        _check(kron, oracle_mod, hp, "pairtile")

@@ -43,6 +43,10 @@ def main():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--ref-gpu", action="store_true")
+    ap.add_argument("--target-mb", type=float, default=0.0,
+                    help="instead of the reference's batch size use a batch whose inputs total this many MB "
+                         "(throughput rather than launch latency); aliasing then is runs of 32 items per output")
+    ap.add_argument("--max-bytes-item", type=float, default=0.0, help="skip shapes whose vector exceeds this many bytes")
     ap.add_argument("--fp64-tflops", type=float, default=34.1)
     ap.add_argument("--fp32-tflops", type=float, default=70.8)
     args = ap.parse_args()
@@ -61,7 +65,15 @@ def main():
         for d in [int(x) for x in args.dims.split(",")]:
             for n in [int(x) for x in args.degrees.split(",")]:
                 nb = batch.compute_batch_size(n, d, level)
-                p = batch.make_problem(d, n, nb, dt, "cuda", seed=993, alias="ref", nb_distinct=5, matrices="reftest")
+                esz = 8 if dt == torch.float64 else 4
+                if args.max_bytes_item and n ** d * esz > args.max_bytes_item:
+                    continue
+                if args.target_mb > 0:
+                    nb = max(64, int(args.target_mb * 1e6 / (n ** d * esz)))
+                    p = batch.make_problem(d, n, nb, dt, "cuda", seed=993, alias="runs", items_per_output=32)
+                else:
+                    p = batch.make_problem(d, n, nb, dt, "cuda", seed=993, alias="ref", nb_distinct=5,
+                                           matrices="reftest")
                 A, i, o, w = p.pointer_arrays()
                 torch.cuda.synchronize()
                 ms = time_call(lambda: api.kronmult_batched(d, n, A, p.lda, i, o, w, nb, dtype=dt, stream=stream),
