@@ -21,9 +21,11 @@
 //    shared memory, touched by the same thread every time -> no synchronisation) and flushed once.
 //    Every flush is REDG, like the reference's atomicAdd (kronmult.cu:126-129).
 //  * Two stages: vector and factors of the next step arrive by cp.async (16-byte chunks when the
-//    item is 16-byte aligned, element-wise otherwise; factors element-wise and transposed on the fly to
-//    row-major with an even pitch, so rows are fetched as broadcast 128-bit loads), pointers one
-//    step further ahead.  Vectors too large for two stages plus the accumulator use one stage.
+//    item is 16-byte aligned, element-wise otherwise; factors stay column-major with a 16-byte column
+//    pitch, so columns are fetched as broadcast 128-bit loads), pointers one step further ahead.
+//    Vectors too large for two stages plus the accumulator use one stage.
+//  * CTAs per SM / streams per CTA / threads are picked at compile time per (T, n, d) from the register
+//    and shared-memory footprints (PairCfg::pick): small CTAs in different phases overlap each other.
 #pragma once
 #include "common.cuh"
 #include "kernel_regtile.cuh" // cp_async_elem / cp_async_commit / cp_async_wait_all
@@ -31,6 +33,11 @@
 
 namespace kron
 {
+
+struct PairPick
+{
+    int minb, stages, acc, B, threads, fits;
+};
 
 template<typename T, int n, int d>
 struct PairCfg
@@ -45,36 +52,79 @@ struct PairCfg
     static constexpr int BLK   = NSQ + PADE;
     static constexpr int ITEM  = TP * BLK;
     static constexpr int ITEMP = (ITEM + VEC - 1) / VEC * VEC; // item pitch: 16-byte multiple
-    static constexpr int RP    = (n + VEC - 1) / VEC * VEC;    // factor row pitch
+    static constexpr int RP    = (n + VEC - 1) / VEC * VEC;    // pitch of a factor column (column-major, as in global)
     static constexpr int MAT   = d * n * RP;
+    // factor pitch per stream: an odd number of 16-byte units, so that the broadcast column loads of lanes that
+    // belong to different streams fall into different banks
+    static constexpr int MATP  = ((MAT / VEC) % 2 == 0) ? MAT + VEC : MAT;
     static constexpr int NPAIR = d / 2;
     static constexpr int ODD   = d % 2;
     static constexpr int NPASS = NPAIR + ODD;
     static constexpr int NCH   = N / VEC; // whole 16-byte chunks of a vector
     static constexpr int TAIL  = N % VEC;
 
-    // two CTAs per SM for the small tiles, one fat CTA otherwise
-    static constexpr int MINB   = (NSQ * S <= 128) ? 2 : 1;
-    static constexpr int BUDGET = (MINB == 2 ? 100 : 200) * 1024;
-    static constexpr int LIMIT  = 220 * 1024;
-    static constexpr int PTRB   = 3 * ((d + 2) * 8 + 4); // three slots of pointers + flag per stream
+    // register tiles: rows are processed in HB blocks so that n^2 + n^2/HB values are live at a time
+    static constexpr int HB   = (S == 8) ? (n >= 7 ? 2 : 1) : (n >= 9 ? 2 : 1);
+    static constexpr int RB   = (n + HB - 1) / HB;
+    static constexpr int REGS = (NSQ + RB * n + n) * (S / 4) + 48; // estimate, checked against ptxas -v
 
-    static constexpr int bytes_item(int stages, int acc) { return (stages + acc) * ITEMP * S + stages * MAT * S + PTRB; }
-    static constexpr int STAGES = bytes_item(2, 1) <= BUDGET ? 2 : 1;
-    static constexpr int ACC    = STAGES == 2 ? 1 : (bytes_item(1, 1) + 64 <= LIMIT ? 1 : 0);
-    static constexpr bool FITS  = bytes_item(STAGES, ACC) + 64 <= LIMIT;
+    static constexpr int PTRB = 3 * ((d + 2) * 8 + 4); // three slots of pointers + flag per stream
+    static constexpr int bytes_item(int stages, int acc) { return (stages + acc) * ITEMP * S + stages * MATP * S + PTRB; }
 
-    static constexpr int bmax() { int b = BUDGET / bytes_item(STAGES, ACC); return b < 1 ? 1 : b; }
-    static constexpr int bwant() { int b = 256 / TP; return b < 1 ? 1 : b; }
-    static constexpr int B      = bwant() < bmax() ? bwant() : bmax();
-    static constexpr int TILES  = B * TP;
-    static constexpr int ITERS  = (TILES + 255) / 256;
-    static constexpr int THREADS = ((TILES + ITERS - 1) / ITERS + 31) / 32 * 32;
+    // CTAs per SM, streams per CTA and threads: as many resident tiles per SM as registers and shared memory
+    // allow, in as many independent CTAs as possible (CTAs in different phases overlap shared-memory traffic,
+    // FMAs and barriers of each other)
+    static constexpr PairPick pick()
+    {
+        int tt = 65536 / REGS;
+        if (tt > 512) tt = 512;
+        tt = tt / 32 * 32;
+        PairPick best{1, 1, 0, 1, 32, 0};
+        int best_total = -1;
+        for (int minb = 8; minb >= 1; --minb)
+        {
+            if (minb == 7 || minb == 5) continue;
+            const int budget = 227 * 1024 / minb - 1024 - 128; // the driver reserves 1 KiB per CTA
+            int cap = (tt / minb) / 32 * 32;
+            if (cap > 256) cap = 256;
+            if (cap < 32) continue;
+            int stages = 2, acc = 1;
+            if (bytes_item(2, 1) > budget)
+            {
+                if (minb > 1) continue;
+                stages = 1;
+                acc    = bytes_item(1, 1) <= budget ? 1 : 0;
+                if (bytes_item(1, acc) > budget) continue;
+            }
+            const int bmax = budget / bytes_item(stages, acc);
+            int B          = TP >= cap ? 1 : cap / TP;
+            if (B > bmax) B = bmax;
+            const int tiles   = B * TP;
+            const int iters   = (tiles + cap - 1) / cap;
+            const int threads = ((tiles + iters - 1) / iters + 31) / 32 * 32;
+            int total         = minb * (tiles / iters);
+            if (total > tt) total = tt;
+            if (total * 10 > best_total * 11) // fewer, fatter CTAs only for >10% more resident tiles
+            {
+                best_total = total;
+                best       = PairPick{minb, stages, acc, B, threads, 1};
+            }
+        }
+        return best;
+    }
+    static constexpr PairPick P = pick();
+    static constexpr int MINB    = P.minb;
+    static constexpr int STAGES  = P.stages;
+    static constexpr int ACC     = P.acc;
+    static constexpr bool FITS   = P.fits != 0;
+    static constexpr int B       = P.B;
+    static constexpr int THREADS = P.threads;
+    static constexpr int TILES   = B * TP;
 
     // byte offsets into dynamic shared memory
     static constexpr int OFF_ACC  = STAGES * B * ITEMP * S;
     static constexpr int OFF_MAT  = OFF_ACC + ACC * B * ITEMP * S;
-    static constexpr int OFF_PTR  = OFF_MAT + STAGES * B * MAT * S; // MAT*S is a 16-byte multiple (RP)
+    static constexpr int OFF_PTR  = OFF_MAT + STAGES * B * MATP * S;
     static constexpr int OFF_FLAG = OFF_PTR + 3 * B * (d + 2) * 8;
     static constexpr int SMEM     = OFF_FLAG + ((3 * B * 4 + 15) / 16) * 16;
 };
@@ -97,12 +147,12 @@ struct PairGeom
     static constexpr int ja    = SINGLE ? 0 : d - 2 - 2 * PASS;
 };
 
-// one row of a factor (row-major, pitch RP) as broadcast 128-bit loads
+// one column of a factor (column-major, pitch RP) as broadcast 128-bit loads
 template<typename T, int n, int RP>
-__device__ __forceinline__ void load_row(const T *__restrict__ row, T (&m)[n])
+__device__ __forceinline__ void load_col(const T *__restrict__ col, T (&m)[n])
 {
     constexpr int VEC = 16 / (int)sizeof(T);
-    const int4 *q = reinterpret_cast<const int4 *>(row);
+    const int4 *q = reinterpret_cast<const int4 *>(col);
 #pragma unroll
     for (int i = 0; i < RP / VEC; ++i)
     {
@@ -123,8 +173,9 @@ __device__ __forceinline__ void load_row(const T *__restrict__ row, T (&m)[n])
 }
 
 // One tile of one pass.  `vec` = the item's vector in shared memory, `acc` = the item's run accumulator,
-// `mats` = the item's d factors, `c` = column index in [0, TP), flag bits: 2 = first item of a run of
-// equal output pointers, 4 = last item of the run.
+// `mats` = the item's d factors (column-major, pitch RP), `c` = column index in [0, TP), flag bits: 2 = first
+// item of a run of equal output pointers, 4 = last item of the run.
+// Both products run with the summation index k outermost: n * RB independent FMA chains advance together.
 template<typename T, int n, int d, int PASS>
 __device__ __forceinline__ void pair_tile(T *__restrict__ vec, T *__restrict__ acc, const T *__restrict__ mats,
                                           int c, int flag, T *__restrict__ outp)
@@ -132,6 +183,8 @@ __device__ __forceinline__ void pair_tile(T *__restrict__ vec, T *__restrict__ a
     using C = PairCfg<T, n, d>;
     using G = PairGeom<T, n, d, PASS>;
     constexpr bool REGFLUSH = G::FINAL && d >= 3; // results leave through REDG straight from registers
+    constexpr bool CONTIG   = (PASS == 0 && !G::SINGLE); // the tile is one contiguous block
+    constexpr int RB        = C::RB;
 
     const int lo = (G::LO > 1) ? c % G::LO : 0;
     const int hi = (G::LO > 1) ? c / G::LO : c;
@@ -140,114 +193,142 @@ __device__ __forceinline__ void pair_tile(T *__restrict__ vec, T *__restrict__ a
     const int base_log = hi * G::sH_log + lo;
     T *__restrict__ x  = vec + base_ph;
 
-    T X[n][n];
-    if constexpr (PASS == 0 && !G::SINGLE && C::VECTILE)
-    {
-        const int4 *q = reinterpret_cast<const int4 *>(x);
-#pragma unroll
-        for (int i = 0; i < C::NSQ / C::VEC; ++i)
-        {
-            const int4 w = q[i];
-            if constexpr (sizeof(T) == 8)
-            {
-                X[(2 * i) / n][(2 * i) % n]         = __hiloint2double(w.y, w.x);
-                X[(2 * i + 1) / n][(2 * i + 1) % n] = __hiloint2double(w.w, w.z);
-            }
-            else
-            {
-                X[(4 * i) / n][(4 * i) % n]         = __int_as_float(w.x);
-                X[(4 * i + 1) / n][(4 * i + 1) % n] = __int_as_float(w.y);
-                X[(4 * i + 2) / n][(4 * i + 2) % n] = __int_as_float(w.z);
-                X[(4 * i + 3) / n][(4 * i + 3) % n] = __int_as_float(w.w);
-            }
-        }
-    }
-    else
-    {
-#pragma unroll
-        for (int a = 0; a < n; ++a)
-#pragma unroll
-            for (int b = 0; b < n; ++b) X[a][b] = x[a * G::sA_ph + b * G::sB_ph];
-    }
-
-    // faster factor along the rows: Z[a][b'] = sum_b Mb(b', b) X[a][b]
+    // faster factor along the rows: Z[a][b'] = sum_k Mb(b', k) X[a][k]
     T Z[n][n];
-    if constexpr (!G::SINGLE)
+#pragma unroll
+    for (int h = 0; h < C::HB; ++h)
     {
-        const T *__restrict__ Mb = mats + G::jb * n * C::RP;
-#pragma unroll
-        for (int bp = 0; bp < n; ++bp)
+        const int a0 = h * RB;
+        T X[RB][n];
+        if constexpr (CONTIG && C::VECTILE && (RB * n) % C::VEC == 0)
         {
-            T m[n];
-            load_row<T, n, C::RP>(Mb + bp * C::RP, m);
+            const int4 *q = reinterpret_cast<const int4 *>(x + a0 * n);
 #pragma unroll
-            for (int a = 0; a < n; ++a)
+            for (int i = 0; i < RB * n / C::VEC; ++i)
             {
-                T dot = X[a][0] * m[0];
-#pragma unroll
-                for (int k = 1; k < n; ++k) dot += X[a][k] * m[k];
-                Z[a][bp] = dot;
-            }
-        }
-    }
-    else
-    {
-#pragma unroll
-        for (int a = 0; a < n; ++a)
-#pragma unroll
-            for (int b = 0; b < n; ++b) Z[a][b] = X[a][b];
-    }
-
-    // slower factor down the columns: Y[a'][b'] = sum_a Ma(a', a) Z[a][b']
-    const T *__restrict__ Ma = mats + G::ja * n * C::RP;
-#pragma unroll
-    for (int ap = 0; ap < n; ++ap)
-    {
-        T m[n];
-        load_row<T, n, C::RP>(Ma + ap * C::RP, m);
-        T y[n];
-#pragma unroll
-        for (int bp = 0; bp < n; ++bp)
-        {
-            T dot = Z[0][bp] * m[0];
-#pragma unroll
-            for (int k = 1; k < n; ++k) dot += Z[k][bp] * m[k];
-            y[bp] = dot;
-        }
-        if constexpr (REGFLUSH)
-        {
-#pragma unroll
-            for (int bp = 0; bp < n; ++bp)
-            {
-                const int ph = base_ph + ap * G::sA_ph + bp * G::sB_ph;
-                const int lg = base_log + ap * G::sA_log + bp * G::sB_log;
-                T v          = y[bp];
-                if constexpr (C::ACC)
-                {
-                    if (!(flag & 2)) v += acc[ph];
-                    if (flag & 4) red_add(outp + lg, v);
-                    else acc[ph] = v;
-                }
-                else { red_add(outp + lg, v); }
-            }
-        }
-        else if constexpr (PASS == 0 && !G::SINGLE && (n % 2) == 0)
-        {
-            // contiguous row of the tile: 2-element stores (n even keeps them aligned)
-#pragma unroll
-            for (int bp = 0; bp < n; bp += 2)
-            {
+                if (a0 * n + i * C::VEC >= C::NSQ) continue;
+                const int4 w = q[i];
                 if constexpr (sizeof(T) == 8)
-                    *reinterpret_cast<double2 *>(x + ap * n + bp) = make_double2(y[bp], y[bp + 1]);
+                {
+                    X[(2 * i) / n][(2 * i) % n]         = __hiloint2double(w.y, w.x);
+                    X[(2 * i + 1) / n][(2 * i + 1) % n] = __hiloint2double(w.w, w.z);
+                }
                 else
-                    *reinterpret_cast<float2 *>(x + ap * n + bp) = make_float2(y[bp], y[bp + 1]);
+                {
+                    X[(4 * i) / n][(4 * i) % n]         = __int_as_float(w.x);
+                    X[(4 * i + 1) / n][(4 * i + 1) % n] = __int_as_float(w.y);
+                    X[(4 * i + 2) / n][(4 * i + 2) % n] = __int_as_float(w.z);
+                    X[(4 * i + 3) / n][(4 * i + 3) % n] = __int_as_float(w.w);
+                }
             }
         }
         else
         {
 #pragma unroll
-            for (int bp = 0; bp < n; ++bp) x[ap * G::sA_ph + bp * G::sB_ph] = y[bp];
+            for (int a = 0; a < RB; ++a)
+#pragma unroll
+                for (int b = 0; b < n; ++b)
+                    if (a0 + a < n) X[a][b] = x[(a0 + a) * G::sA_ph + b * G::sB_ph];
         }
+        if constexpr (!G::SINGLE)
+        {
+            const T *__restrict__ Mb = mats + G::jb * n * C::RP;
+#pragma unroll
+            for (int k = 0; k < n; ++k)
+            {
+                T m[n];
+                load_col<T, n, C::RP>(Mb + k * C::RP, m);
+#pragma unroll
+                for (int a = 0; a < RB; ++a)
+#pragma unroll
+                    for (int bp = 0; bp < n; ++bp)
+                        if (a0 + a < n) Z[a0 + a][bp] = (k == 0) ? X[a][0] * m[bp] : fma(X[a][k], m[bp], Z[a0 + a][bp]);
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int a = 0; a < RB; ++a)
+#pragma unroll
+                for (int b = 0; b < n; ++b)
+                    if (a0 + a < n) Z[a0 + a][b] = X[a][b];
+        }
+    }
+
+    // slower factor down the columns: Y[a'][b'] = sum_k Ma(a', k) Z[k][b']
+    const T *__restrict__ Ma = mats + G::ja * n * C::RP;
+#pragma unroll
+    for (int h = 0; h < C::HB; ++h)
+    {
+        const int a0 = h * RB;
+        T Y[RB][n];
+#pragma unroll
+        for (int k = 0; k < n; ++k)
+        {
+            T m[n];
+            load_col<T, n, C::RP>(Ma + k * C::RP, m);
+#pragma unroll
+            for (int a = 0; a < RB; ++a)
+#pragma unroll
+                for (int bp = 0; bp < n; ++bp)
+                    if (a0 + a < n) Y[a][bp] = (k == 0) ? Z[0][bp] * m[a0 + a] : fma(Z[k][bp], m[a0 + a], Y[a][bp]);
+        }
+#pragma unroll
+        for (int a = 0; a < RB; ++a)
+        {
+            const int ap = a0 + a;
+            if (ap >= n) continue;
+            if constexpr (REGFLUSH)
+            {
+#pragma unroll
+                for (int bp = 0; bp < n; ++bp)
+                {
+                    const int ph = base_ph + ap * G::sA_ph + bp * G::sB_ph;
+                    const int lg = base_log + ap * G::sA_log + bp * G::sB_log;
+                    T v          = Y[a][bp];
+                    if constexpr (C::ACC)
+                    {
+                        if (!(flag & 2)) v += acc[ph];
+                        if (flag & 4) red_add(outp + lg, v);
+                        else acc[ph] = v;
+                    }
+                    else { red_add(outp + lg, v); }
+                }
+            }
+            else if constexpr (CONTIG && (n % 2) == 0)
+            {
+                // contiguous row of the tile: 2-element stores (n even keeps them aligned)
+#pragma unroll
+                for (int bp = 0; bp < n; bp += 2)
+                {
+                    if constexpr (sizeof(T) == 8)
+                        *reinterpret_cast<double2 *>(x + ap * n + bp) = make_double2(Y[a][bp], Y[a][bp + 1]);
+                    else
+                        *reinterpret_cast<float2 *>(x + ap * n + bp) = make_float2(Y[a][bp], Y[a][bp + 1]);
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int bp = 0; bp < n; ++bp) x[ap * G::sA_ph + bp * G::sB_ph] = Y[a][bp];
+            }
+        }
+    }
+}
+
+// Work distribution of the copy loops: groups of GL lanes (a power of two, or the whole CTA when there is a single
+// stream) walk the streams, f(b, gl, GL) then loops over the stream's PER_ITEM pieces from gl in steps of GL -- the
+// per-stream values (flag, pointers, alignment) are fetched once per stream and no division by PER_ITEM is needed.
+template<int PER_ITEM, int B, int THREADS, typename F>
+__device__ __forceinline__ void for_items(int tid, F f)
+{
+    if constexpr (B == 1) { f(0, tid, THREADS); }
+    else
+    {
+        constexpr int GL = PER_ITEM >= 32 ? 32 : (PER_ITEM > 16 ? 32 : (PER_ITEM > 8 ? 16 : (PER_ITEM > 4 ? 8 : (PER_ITEM > 2 ? 4 : (PER_ITEM > 1 ? 2 : 1)))));
+        constexpr int GROUPS = THREADS / GL;
+        const int g = tid / GL, gl = tid % GL;
+        for (int b = g; b < B; b += GROUPS) f(b, gl, GL);
     }
 }
 
@@ -258,7 +339,7 @@ __device__ __forceinline__ void pair_passes(unsigned char *smem, int stage, cons
     using C = PairCfg<T, n, d>;
     T *vecs       = reinterpret_cast<T *>(smem) + (size_t)stage * C::B * C::ITEMP;
     T *accs       = reinterpret_cast<T *>(smem + C::OFF_ACC);
-    const T *mats = reinterpret_cast<const T *>(smem + C::OFF_MAT) + (size_t)stage * C::B * C::MAT;
+    const T *mats = reinterpret_cast<const T *>(smem + C::OFF_MAT) + (size_t)stage * C::B * C::MATP;
 #pragma unroll 1
     for (int tl = threadIdx.x; tl < C::TILES; tl += C::THREADS)
     {
@@ -266,7 +347,7 @@ __device__ __forceinline__ void pair_passes(unsigned char *smem, int stage, cons
         const int c    = (C::B > 1) ? tl - b * C::TP : tl;
         const int flag = s_flag[b];
         if (flag)
-            pair_tile<T, n, d, PASS>(vecs + b * C::ITEMP, accs + b * C::ITEMP, mats + b * C::MAT, c, flag,
+            pair_tile<T, n, d, PASS>(vecs + b * C::ITEMP, accs + b * C::ITEMP, mats + b * C::MATP, c, flag,
                                      s_ptr[b * (d + 2) + d + 1]);
     }
     if constexpr (PASS + 1 < C::NPASS)
@@ -332,52 +413,74 @@ __global__ void __launch_bounds__(PairCfg<T, n, d>::THREADS, PairCfg<T, n, d>::M
         T *const *sp  = slot_ptrs(t % 3);
         const int *sf = slot_flag(t % 3);
         T *vecs       = reinterpret_cast<T *>(smem) + (size_t)stage * C::B * C::ITEMP;
-        T *mats       = reinterpret_cast<T *>(smem + C::OFF_MAT) + (size_t)stage * C::B * C::MAT;
-        if constexpr (C::NCH > 0)
-        {
-            for (int e = tid; e < C::B * C::NCH; e += C::THREADS)
+        T *mats       = reinterpret_cast<T *>(smem + C::OFF_MAT) + (size_t)stage * C::B * C::MATP;
+        // the vector: 16-byte chunks (padded destination) when the item is 16-byte aligned, element-wise otherwise
+        for_items<(C::NCH > 0 ? C::NCH : 1), C::B, C::THREADS>(tid, [&](int b, int gl, int GL) {
+            if (!sf[b]) return;
+            const T *src = sp[b * (d + 2) + d];
+            T *dst       = vecs + b * C::ITEMP;
+            if (aligned16(src))
             {
-                const int b = (C::B > 1) ? e / C::NCH : 0;
-                const int q = (C::B > 1) ? e - b * C::NCH : e;
-                if (!sf[b]) continue;
-                const T *src = sp[b * (d + 2) + d] + q * C::VEC;
-                int el       = q * C::VEC;
-                if constexpr (C::PADE > 0) el += (el / C::NSQ) * C::PADE;
-                T *dst = vecs + b * C::ITEMP + el;
-                if (aligned16(src))
+                for (int q = gl; q < C::NCH; q += GL)
                 {
-                    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dst);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
+                    int el = q * C::VEC;
+                    if constexpr (C::PADE > 0) el += (q / (C::NSQ / C::VEC)) * C::PADE;
+                    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dst + el);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + q * C::VEC) : "memory");
                 }
-                else
+                for (int i = C::NCH * C::VEC + gl; i < C::N; i += GL) cp_async_elem<T>(dst + i, src + i); // no pad here
+            }
+            else
+            {
+                for (int i = gl; i < C::N; i += GL)
                 {
+                    int el = i;
+                    if constexpr (C::PADE > 0) el += (i / C::NSQ) * C::PADE;
+                    cp_async_elem<T>(dst + el, src + i);
+                }
+            }
+        });
+        // factors stay column-major (pitch RP): whole 16-byte chunks of a column when n, lda and the base address
+        // allow it, element-wise otherwise
+        constexpr int CPC = (n % C::VEC == 0) ? n / C::VEC : 1; // chunks per column
+        const bool lda_ok = (n % C::VEC == 0) && (lda % C::VEC == 0);
+        for_items<d * C::NSQ, C::B, C::THREADS>(tid, [&](int b, int gl, int GL) {
+            if (!sf[b]) return;
+            if (lda_ok)
+            {
+                for (int r = gl; r < d * n * CPC; r += GL)
+                {
+                    const int j  = r / (n * CPC);
+                    const int rc = r - j * (n * CPC);
+                    const int cc = rc / CPC;
+                    const int q  = rc - cc * CPC;
+                    const T *src = sp[b * (d + 2) + j] + (long long)cc * lda + q * C::VEC;
+                    T *dst       = mats + b * C::MATP + j * n * C::RP + cc * C::RP + q * C::VEC;
+                    if (aligned16(src))
+                    {
+                        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dst);
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
+                    }
+                    else
+                    {
 #pragma unroll
-                    for (int i = 0; i < C::VEC; ++i) cp_async_elem<T>(dst + i, src + i);
+                        for (int i = 0; i < C::VEC; ++i) cp_async_elem<T>(dst + i, src + i);
+                    }
                 }
             }
-        }
-        if constexpr (C::TAIL > 0)
-        {
-            for (int e = tid; e < C::B * C::TAIL; e += C::THREADS)
+            else
             {
-                const int b = e / C::TAIL;
-                const int i = C::NCH * C::VEC + (e - b * C::TAIL);
-                if (!sf[b]) continue;
-                cp_async_elem<T>(vecs + b * C::ITEMP + i, sp[b * (d + 2) + d] + i); // TAIL > 0 only without padding
+                for (int r = gl; r < d * C::NSQ; r += GL)
+                {
+                    const int j  = r / C::NSQ;
+                    const int rc = r - j * C::NSQ;
+                    const int cc = rc / n;
+                    const int rr = rc - cc * n;
+                    cp_async_elem<T>(mats + b * C::MATP + j * n * C::RP + cc * C::RP + rr,
+                                     sp[b * (d + 2) + j] + rr + (long long)cc * lda);
+                }
             }
-        }
-        for (int e = tid; e < C::B * d * C::NSQ; e += C::THREADS)
-        {
-            const int b  = e / (d * C::NSQ);
-            const int r  = e - b * (d * C::NSQ);
-            const int j  = r / C::NSQ;
-            const int rc = r - j * C::NSQ;
-            const int cc = rc / n;
-            const int rr = rc - cc * n;
-            if (!sf[b]) continue;
-            const T *Ap = sp[b * (d + 2) + j];
-            cp_async_elem<T>(mats + b * C::MAT + j * n * C::RP + rr * C::RP + cc, Ap + rr + (long long)cc * lda);
-        }
+        });
         cp_async_commit();
     };
 

@@ -240,10 +240,16 @@ static cudaError_t run_tiny(int d, int n, const T *const *A, int lda, T *const *
 {
 #define KRON_TINY(NN, DD) \
     if (n == NN && d == DD) return launch_tiny<T, NN, DD>(A, lda, in, out, nb, st);
-    KRON_TINY(2, 1) KRON_TINY(2, 2) KRON_TINY(2, 3) KRON_TINY(2, 4)
-    KRON_TINY(3, 1) KRON_TINY(3, 2)
-    KRON_TINY(4, 1) KRON_TINY(4, 2)
+    KRON_TINY(2, 1) KRON_TINY(2, 2) KRON_TINY(2, 3) KRON_TINY(2, 4) KRON_TINY(2, 5) KRON_TINY(2, 6)
+    KRON_TINY(3, 1) KRON_TINY(3, 2) KRON_TINY(3, 3)
+    KRON_TINY(4, 1) KRON_TINY(4, 2) KRON_TINY(4, 3)
     KRON_TINY(5, 1) KRON_TINY(6, 1) KRON_TINY(7, 1) KRON_TINY(8, 1) KRON_TINY(9, 1) KRON_TINY(10, 1)
+    KRON_TINY(5, 2) KRON_TINY(6, 2)
+    if constexpr (sizeof(T) == 4)
+    {
+        // vector + one factor in registers: 2 n^2 values for d = 2
+        KRON_TINY(7, 2) KRON_TINY(8, 2) KRON_TINY(9, 2) KRON_TINY(10, 2) KRON_TINY(3, 4) KRON_TINY(5, 3)
+    }
 #undef KRON_TINY
     return cudaErrorNotSupported;
 }
