@@ -43,6 +43,25 @@ int kronmult_batched_f64_async(int d, int n, const double *const *A, int lda, do
 int kronmult_batched_f32_async(int d, int n, const float *const *A, int lda, float **in, float **out,
                                float **ws, int nb, void *stream);
 
+/* Read-only-input variants (no reference counterpart).  The reference's contract lets
+ * the call clobber `input` (kronmult.cuh:23, kronmult.cu:115-121), which forces an ASGarD-style caller to give every
+ * batch item its own copy of its input vector.  Here `in[k]` is never written, so items may share input vectors
+ * (in[k] may repeat, like out[k]): a vector that many items multiply is fetched from HBM once and served from L2.
+ * `ws[k]` must be a distinct n^d-element scratch vector per item when kronmult_b200_needs_workspace(d, n, sizeof(T))
+ * returns 1 (vectors too long for shared memory take a multi-pass route through global memory: the first pass writes
+ * the scratch vector, the rest works in place there); otherwise `ws` is not dereferenced and may be NULL.  With a
+ * needed but missing `ws` the call fails with cudaErrorInvalidValue.  Everything else as kronmult_batched_*. */
+int kronmult_batched_const_f64(int d, int n, const double *const *A, int lda, const double *const *in, double **out,
+                               double **ws, int nb);
+int kronmult_batched_const_f32(int d, int n, const float *const *A, int lda, const float *const *in, float **out,
+                               float **ws, int nb);
+int kronmult_batched_const_f64_async(int d, int n, const double *const *A, int lda, const double *const *in,
+                                     double **out, double **ws, int nb, void *stream);
+int kronmult_batched_const_f32_async(int d, int n, const float *const *A, int lda, const float *const *in, float **out,
+                                     float **ws, int nb, void *stream);
+/* 1 if the read-only-input entry points need `ws` for this shape, 0 if not, -1 for invalid arguments */
+int kronmult_b200_needs_workspace(int d, int n, int elem_size);
+
 /* Host-buffer entry points with the signature of the reference's CPU flavour
  * (kronmult_omp/kronmult.hpp:77-80): every pointer array and every pointee lives in HOST memory.
  * The library stages chunks of items through pinned buffers, runs the device path on `device`

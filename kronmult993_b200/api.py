@@ -38,6 +38,11 @@ C_SYMBOLS = (
     "kronmult_partition_by_output",
     "kronmult_plan_create_f64",
     "kronmult_plan_create_f32",
+    "kronmult_batched_const_f64",
+    "kronmult_batched_const_f32",
+    "kronmult_batched_const_f64_async",
+    "kronmult_batched_const_f32_async",
+    "kronmult_b200_needs_workspace",
     "kronmult_plan_execute",
     "kronmult_plan_stats",
     "kronmult_plan_destroy",
@@ -97,6 +102,13 @@ def load_library() -> ctypes.CDLL:
         f.restype, f.argtypes = c_int, [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int]
         f = getattr(lib, f"kronmult_plan_create_{sfx}")
         f.restype, f.argtypes = c_int, [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_vp, ctypes.POINTER(c_vp)]
+    for sfx in ("f64", "f32"):
+        f = getattr(lib, f"kronmult_batched_const_{sfx}")
+        f.restype, f.argtypes = c_int, [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int]
+        f = getattr(lib, f"kronmult_batched_const_{sfx}_async")
+        f.restype, f.argtypes = c_int, [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp]
+    lib.kronmult_b200_needs_workspace.restype = c_int
+    lib.kronmult_b200_needs_workspace.argtypes = [c_int, c_int, c_int]
     lib.kronmult_plan_execute.restype, lib.kronmult_plan_execute.argtypes = c_int, [c_vp, c_vp]
     lib.kronmult_plan_stats.restype = c_int
     lib.kronmult_plan_stats.argtypes = [c_vp, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong),
@@ -161,6 +173,33 @@ def kronmult_batched(matrix_count: int, matrix_size: int, matrix_list_batched, m
         code = getattr(lib, f"kronmult_batched_{sfx}_async")(*args, handle)
     if code != 0:
         raise KronmultError(code, "kronmult_batched")
+
+
+def kronmult_batched_const(matrix_count: int, matrix_size: int, matrix_list_batched, matrix_stride: int, input_batched,
+                           output_batched, workspace_batched, nb_batch: int, *, dtype=torch.float64,
+                           stream: Union[None, int, "torch.cuda.Stream"] = None) -> None:
+    """Read-only-input variant (``kronmult_batched_const_*`` of ``include/kronmult_b200.h``): ``input[k]`` is never
+    written, so entries of ``input_batched`` may repeat; ``workspace_batched`` may be ``None`` unless
+    ``needs_workspace(matrix_count, matrix_size, dtype)``."""
+    lib = load_library()
+    sfx = _suffix(dtype)
+    args = [int(matrix_count), int(matrix_size), _addr(matrix_list_batched), int(matrix_stride),
+            _addr(input_batched), _addr(output_batched), _addr(workspace_batched), int(nb_batch)]
+    if stream is None:
+        code = getattr(lib, f"kronmult_batched_const_{sfx}")(*args)
+    else:
+        handle = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+        code = getattr(lib, f"kronmult_batched_const_{sfx}_async")(*args, handle)
+    if code != 0:
+        raise KronmultError(code, "kronmult_batched_const")
+
+
+def needs_workspace(matrix_count: int, matrix_size: int, dtype=torch.float64) -> bool:
+    r = load_library().kronmult_b200_needs_workspace(int(matrix_count), int(matrix_size),
+                                                     8 if _suffix(dtype) == "f64" else 4)
+    if r < 0:
+        raise ValueError("invalid shape")
+    return bool(r)
 
 
 def kronmult_batched_host(matrix_count: int, matrix_size: int, matrix_list_batched, matrix_stride: int,

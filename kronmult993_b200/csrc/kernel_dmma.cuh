@@ -276,8 +276,9 @@ static cudaError_t launch_dmma84(int sms, const double *const *A, int lda, doubl
 // written by one warp instruction pair), phase 2 works in place too, and the write-back streams the slot
 // linearly to global memory.  Factor fragments are fetched one unit ahead, their pointers two.
 __global__ void __launch_bounds__(Dmma84::THREADS, 2)
-kron_dmma8_tile4_kernel(const double *const *__restrict__ A, double *const *__restrict__ in, const int lda,
-                        const int d, const int tiles_per_item, const long long total_units)
+kron_dmma8_tile4_kernel(const double *const *__restrict__ A, double *const *__restrict__ in,
+                        double *const *__restrict__ dst, const int lda, const int d, const int tiles_per_item,
+                        const long long total_units)
 {
     using C = Dmma84;
     constexpr int N = C::N, T1 = C::T1, P2 = C::P2, NST = 3;
@@ -336,6 +337,10 @@ kron_dmma8_tile4_kernel(const double *const *__restrict__ A, double *const *__re
         double *Ec        = R + slot * N;
         double *base      = tile_ptr(u);
         const bool vec    = aligned16(base);
+        // results go back over the tile (dst == in: the reference's clobbering contract) or into the per-item
+        // scratch vector of the read-only-input entry points
+        double *wb        = dst[u / tiles_per_item] + (u % tiles_per_item) * N;
+        const bool vecw   = aligned16(wb);
         double a[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) a[i] = a_nxt[i];
@@ -397,8 +402,8 @@ kron_dmma8_tile4_kernel(const double *const *__restrict__ A, double *const *__re
             const int c  = t + i * C::THREADS;
             const int h  = c >> 5;
             const double2 v = *reinterpret_cast<const double2 *>(Ec + h * 64 + (((c & 31) ^ dmma_sigma(h)) << 1));
-            if (vec) *reinterpret_cast<double2 *>(base + 2 * c) = v;
-            else { base[2 * c] = v.x; base[2 * c + 1] = v.y; }
+            if (vecw) *reinterpret_cast<double2 *>(wb + 2 * c) = v;
+            else { wb[2 * c] = v.x; wb[2 * c + 1] = v.y; }
         }
     }
 }
@@ -513,6 +518,7 @@ kron_dmma8_rows2_kernel(const double *const *__restrict__ A, double *const *__re
 // pass A for n = 8, d >= 5: the four fastest factors, in place
 static constexpr int TILE4_SMEM = 3 * Dmma84::N * 8 + 64;
 static cudaError_t launch_dmma8_tile4(int sms, int d, long long N, const double *const *A, int lda, double *const *in,
+                                      double *const *dst,
                                       int nb, cudaStream_t st, std::atomic<long long> &launches)
 {
     using C = Dmma84;
@@ -527,7 +533,7 @@ static cudaError_t launch_dmma8_tile4(int sms, int d, long long N, const double 
     const long long units    = (long long)nb * tpi;
     const long long max_grid = (long long)sms * 2;
     const int grid           = (int)(units < max_grid ? units : max_grid);
-    kron_dmma8_tile4_kernel<<<grid, C::THREADS, TILE4_SMEM, st>>>(A, in, lda, d, tpi, units);
+    kron_dmma8_tile4_kernel<<<grid, C::THREADS, TILE4_SMEM, st>>>(A, in, dst, lda, d, tpi, units);
     launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
@@ -561,7 +567,8 @@ static cudaError_t launch_dmma8_rows2(int sms, int d, long long N, const double 
 // d = 5 returns cudaSuccess after pass A with *remaining = 1: the caller applies factor 0 (generic pass).
 template<typename T>
 static cudaError_t run_dmma(int sms, int d, int n, const T *const *A, int lda, T *const *in, T *const *out, int nb,
-                            cudaStream_t st, std::atomic<long long> &launches, const char *&last_path, int *remaining)
+                            cudaStream_t st, std::atomic<long long> &launches, const char *&last_path, int *remaining,
+                            T *const *scratch = nullptr)
 {
     *remaining = 0;
     if constexpr (sizeof(T) == 8)
@@ -575,9 +582,11 @@ static cudaError_t run_dmma(int sms, int d, int n, const T *const *A, int lda, T
         {
             const long long N = (d == 5) ? 32768 : 262144;
             last_path = "dmma-multipass";
-            cudaError_t e = launch_dmma8_tile4(sms, d, N, A, lda, in, nb, st, launches);
+            // scratch != nullptr: `in` is read-only, pass A writes into the scratch vectors and the rest works there
+            T *const *work = scratch ? scratch : in;
+            cudaError_t e  = launch_dmma8_tile4(sms, d, N, A, lda, in, work, nb, st, launches);
             if (e != cudaSuccess) return e;
-            if (d == 6) return launch_dmma8_rows2(sms, d, N, A, lda, in, out, nb, st, launches);
+            if (d == 6) return launch_dmma8_rows2(sms, d, N, A, lda, work, out, nb, st, launches);
             *remaining = 1;
             return cudaSuccess;
         }

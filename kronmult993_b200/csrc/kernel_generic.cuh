@@ -30,6 +30,7 @@ struct PassParams
 {
     const T *const *A;
     T *const *in;
+    T *const *dst;            // where a non-final pass stores its result: == in (in place) or the scratch vectors
     T *const *out;
     int d, n, lda, nb;
     int j0, G;                // this pass applies factors j0 .. j0+G-1 (highest index first)
@@ -88,7 +89,8 @@ __global__ void __launch_bounds__(256) kron_pass_kernel(const PassParams<T> p)
     T *mats        = reinterpret_cast<T *>(smem + p.off_mats);
     T **s_in       = reinterpret_cast<T **>(smem + p.off_ptrs);
     T **s_out      = s_in + p.B;
-    const T **s_A  = static_cast<const T **>(static_cast<void *>(s_out + p.B));
+    T **s_dst      = s_out + p.B;
+    const T **s_A  = static_cast<const T **>(static_cast<void *>(s_dst + p.B));
     int *s_flag    = reinterpret_cast<int *>(s_A + p.B * p.G);
     const int n    = NT > 0 ? NT : p.n;
     const int nn   = n * n;
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(256) kron_pass_kernel(const PassParams<T> p)
                 {
                     T *o     = p.out[k];
                     s_in[b]  = p.in[k];
+                    s_dst[b] = p.dst[k];
                     s_out[b] = o;
                     // bit1: first item of a run of equal output pointers (within this stream)
                     // bit2: last item of the run -> flush the shared-memory sum
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(256) kron_pass_kernel(const PassParams<T> p)
                 const int l = r - m * p.LB;
                 const long long gi = tile_base + (long long)m * p.L + l;
                 const T v = buf[e];
-                if (!p.final_pass) { s_in[b][gi] = v; }
+                if (!p.final_pass) { s_dst[b][gi] = v; }
                 else if (p.use_acc)
                 {
                     const T a = (flag & 2) ? v : acc[e] + v;

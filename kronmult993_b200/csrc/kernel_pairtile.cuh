@@ -88,26 +88,31 @@ struct PairCfg
             int cap = (tt / minb) / 32 * 32;
             if (cap > 256) cap = 256;
             if (cap < 32) continue;
-            int stages = 2, acc = 1;
-            if (bytes_item(2, 1) > budget)
+            // one stage suffices when >= 3 CTAs share the SM (the others' work hides the load); a single fat CTA falls
+            // back to one stage (and no accumulator) only when nothing else fits
+            for (int stages = 2; stages >= 1; --stages)
             {
-                if (minb > 1) continue;
-                stages = 1;
-                acc    = bytes_item(1, 1) <= budget ? 1 : 0;
-                if (bytes_item(1, acc) > budget) continue;
-            }
-            const int bmax = budget / bytes_item(stages, acc);
-            int B          = TP >= cap ? 1 : cap / TP;
-            if (B > bmax) B = bmax;
-            const int tiles   = B * TP;
-            const int iters   = (tiles + cap - 1) / cap;
-            const int threads = ((tiles + iters - 1) / iters + 31) / 32 * 32;
-            int total         = minb * (tiles / iters);
-            if (total > tt) total = tt;
-            if (total * 10 > best_total * 11) // fewer, fatter CTAs only for >10% more resident tiles
-            {
-                best_total = total;
-                best       = PairPick{minb, stages, acc, B, threads, 1};
+                int acc = 1;
+                if (stages == 1 && minb < 3 && bytes_item(2, 1) <= budget) continue;
+                if (bytes_item(stages, 1) > budget)
+                {
+                    if (minb > 1 || stages == 2) continue;
+                    acc = 0;
+                    if (bytes_item(1, 0) > budget) continue;
+                }
+                const int bmax = budget / bytes_item(stages, acc);
+                int B          = TP >= cap ? 1 : cap / TP;
+                if (B > bmax) B = bmax;
+                const int tiles   = B * TP;
+                const int iters   = (tiles + cap - 1) / cap;
+                const int threads = ((tiles + iters - 1) / iters + 31) / 32 * 32;
+                int total         = minb * (tiles / iters);
+                if (total > tt) total = tt;
+                if (total * 10 > best_total * 11) // fewer, fatter CTAs only for >10% more resident tiles
+                {
+                    best_total = total;
+                    best       = PairPick{minb, stages, acc, B, threads, 1};
+                }
             }
         }
         return best;
@@ -543,12 +548,29 @@ __global__ void __launch_bounds__(PairCfg<T, n, d>::THREADS, PairCfg<T, n, d>::M
 // host side
 // ----------------------------------------------------------------------------------------------
 template<typename T, int n, int d>
+constexpr bool pairtile_has() { return PairCfg<T, n, d>::FITS && !(sizeof(T) == 8 && n > 8); }
+template<typename T>
+static bool pairtile_fits(int d, int n)
+{
+    switch (n * 16 + d)
+    {
+#define KRON_PTF(NN, DD) case NN * 16 + DD: return pairtile_has<T, NN, DD>();
+#define KRON_PTF_N(NN) KRON_PTF(NN, 2) KRON_PTF(NN, 3) KRON_PTF(NN, 4) KRON_PTF(NN, 5) KRON_PTF(NN, 6)
+        KRON_PTF_N(2) KRON_PTF_N(3) KRON_PTF_N(4) KRON_PTF_N(5) KRON_PTF_N(6) KRON_PTF_N(7) KRON_PTF_N(8) KRON_PTF_N(9)
+        KRON_PTF_N(10)
+#undef KRON_PTF_N
+#undef KRON_PTF
+    default: return false;
+    }
+}
+
+template<typename T, int n, int d>
 static cudaError_t launch_pairtile(int sms, const T *const *A, int lda, T *const *in, T *const *out, int nb,
                                    cudaStream_t st, std::atomic<long long> &launches)
 {
     using C = PairCfg<T, n, d>;
     // fp64 tiles of n >= 9 do not fit the register file (2 n^2 live values)
-    if constexpr (!C::FITS || (sizeof(T) == 8 && n > 8)) { return cudaErrorNotSupported; }
+    if constexpr (!pairtile_has<T, n, d>()) { return cudaErrorNotSupported; }
     else
     {
         auto kfn = kron_pairtile_kernel<T, n, d>;

@@ -90,7 +90,7 @@ static bool fill_pass(PassParams<T> &p, int &smem, int &grid, const DeviceInfo &
         int o_acc  = align_up(b * p.tile_elems * s, 16);
         int o_mats = o_acc + (acc ? align_up(b * p.tile_elems * s, 16) : 0);
         int o_ptrs = o_mats + align_up(b * p.G * p.n * p.n * s, 16);
-        return o_ptrs + b * (2 + p.G) * 8 + align_up(b * 4, 16);
+        return o_ptrs + b * (3 + p.G) * 8 + align_up(b * 4, 16);
     };
     p.use_acc = p.final_pass ? 1 : 0;
     while (B > 1 && bytes(B, p.use_acc) > budget) B /= 2;
@@ -121,7 +121,8 @@ static bool fill_pass(PassParams<T> &p, int &smem, int &grid, const DeviceInfo &
 
 template<typename T>
 static cudaError_t plan_generic(GenericPlan<T> &plan, const DeviceInfo &di, int d, int n, const T *const *A, int lda,
-                                T *const *in, T *const *out, int nb, int fast_done = 0)
+                                T *const *in, T *const *out, int nb, int fast_done = 0, T *const *scratch = nullptr,
+                                bool in_is_scratch = false)
 {
     if (n < 1 || n > 32 || d < 0) return cudaErrorInvalidValue;
     long long N = 1;
@@ -132,7 +133,7 @@ static cudaError_t plan_generic(GenericPlan<T> &plan, const DeviceInfo &di, int 
     }
     const int s = (int)sizeof(T);
     PassParams<T> base{};
-    base.A = A; base.in = in; base.out = out;
+    base.A = A; base.in = in; base.dst = in; base.out = out;
     base.d = d; base.n = n; base.lda = lda; base.nb = nb;
 
     const int resident_budget = 96 * 1024;           // two CTAs per SM when the accumulator fits
@@ -173,6 +174,14 @@ static cudaError_t plan_generic(GenericPlan<T> &plan, const DeviceInfo &di, int 
         while (LB * n <= L && M * LB * n <= cap) LB *= n;
         p.j0 = d - done - G; p.G = G; p.Mext = (int)M; p.L = L; p.LB = (int)LB;
         p.final_pass = (done + G == d) ? 1 : 0;
+        if (scratch)
+        {
+            // read-only input: the first pass of the whole product reads `in` and writes the scratch vectors, every
+            // later pass works in place there
+            const bool first = (np == 0) && !in_is_scratch;
+            p.in  = first ? in : scratch;
+            p.dst = scratch;
+        }
         if (!fill_pass(p, plan.smem[np], plan.grid[np], di, N, resident_budget)) return cudaErrorInvalidValue;
         plan.pass[np++] = p;
         done += G;
@@ -197,11 +206,14 @@ static cudaError_t launch_pass(const PassParams<T> &p, int grid, int smem, cudaS
 
 template<typename T>
 static cudaError_t run_generic(const DeviceInfo &di, int d, int n, const T *const *A, int lda, T *const *in,
-                               T *const *out, int nb, cudaStream_t st, int fast_done = 0)
+                               T *const *out, int nb, cudaStream_t st, int fast_done = 0, T *const *scratch = nullptr,
+                               bool const_in = false)
 {
     GenericPlan<T> plan;
-    cudaError_t e = plan_generic<T>(plan, di, d, n, A, lda, in, out, nb, fast_done);
+    // fast_done > 0: an earlier kernel already moved the vector into the scratch vectors (when there are any)
+    cudaError_t e = plan_generic<T>(plan, di, d, n, A, lda, in, out, nb, fast_done, scratch, fast_done > 0);
     if (e != cudaSuccess) return e;
+    if (const_in && !scratch && (plan.npass > 1 || fast_done > 0)) return cudaErrorInvalidValue; // would clobber `in`
     for (int i = 0; i < plan.npass; ++i)
     {
         const PassParams<T> &p = plan.pass[i];
@@ -242,6 +254,7 @@ static cudaError_t run_tiny(int d, int n, const T *const *A, int lda, T *const *
     if (n == NN && d == DD) return launch_tiny<T, NN, DD>(A, lda, in, out, nb, st);
     KRON_TINY(2, 1) KRON_TINY(2, 2) KRON_TINY(2, 3) KRON_TINY(2, 4) KRON_TINY(2, 5) KRON_TINY(2, 6)
     KRON_TINY(3, 1) KRON_TINY(3, 2) KRON_TINY(3, 3)
+    if constexpr (sizeof(T) == 8) { KRON_TINY(3, 4) } // 81 doubles + one 3x3 factor: 162 + 18 registers
     KRON_TINY(4, 1) KRON_TINY(4, 2) KRON_TINY(4, 3)
     KRON_TINY(5, 1) KRON_TINY(6, 1) KRON_TINY(7, 1) KRON_TINY(8, 1) KRON_TINY(9, 1) KRON_TINY(10, 1)
     KRON_TINY(5, 2) KRON_TINY(6, 2)
@@ -259,8 +272,12 @@ static cudaError_t run_tiny(int d, int n, const T *const *A, int lda, T *const *
 // ----------------------------------------------------------------------------------------------
 template<typename T>
 static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *in, T *const *out, int nb,
-                            cudaStream_t st)
+                            cudaStream_t st, bool const_in = false, T *const *scratch = nullptr)
 {
+    // const_in: the read-only-input entry points (kronmult_batched_const_*).  `in` is never written; the routes that
+    // work in place through global memory (vectors beyond shared memory) use the per-item scratch vectors instead
+    // and fail with cudaErrorInvalidValue when there are none.  Otherwise scratch stays nullptr: in place in `in`.
+    if (!const_in) scratch = nullptr;
     if (nb <= 0) return cudaSuccess; // the reference launches an empty grid (kronmult.cu:191) -> no-op
     if (d < 0 || n < 1 || lda < n || (!A && d > 0) || !in || !out) return cudaErrorInvalidValue;
     DeviceInfo di;
@@ -268,7 +285,7 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
     if (e != cudaSuccess) return e;
 
     const int force = g_force.load(std::memory_order_relaxed);
-    if (force == PATH_GENERIC) return run_generic<T>(di, d, n, A, lda, in, out, nb, st);
+    if (force == PATH_GENERIC) return run_generic<T>(di, d, n, A, lda, in, out, nb, st, 0, scratch, const_in);
     if (force == PATH_TINY)
     {
         e = run_tiny<T>(d, n, A, lda, in, out, nb, st);
@@ -298,8 +315,10 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
     if (force == PATH_DMMA)
     {
         int remaining = 0;
-        e = run_dmma<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path, &remaining);
-        if (e == cudaSuccess && remaining > 0) e = run_generic<T>(di, d, n, A, lda, in, out, nb, st, d - remaining);
+        if (const_in && !scratch && n == 8 && d > 4) return cudaErrorInvalidValue;
+        e = run_dmma<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path, &remaining, scratch);
+        if (e == cudaSuccess && remaining > 0)
+            e = run_generic<T>(di, d, n, A, lda, in, out, nb, st, d - remaining, scratch, const_in);
         return e == cudaErrorNotSupported ? cudaErrorInvalidValue : e;
     }
 
@@ -308,8 +327,10 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
     if (e != cudaErrorNotSupported) return e;
     {
         int remaining = 0;
-        e = run_dmma<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path, &remaining);
-        if (e == cudaSuccess && remaining > 0) e = run_generic<T>(di, d, n, A, lda, in, out, nb, st, d - remaining);
+        if (const_in && !scratch && sizeof(T) == 8 && n == 8 && d > 4) return cudaErrorInvalidValue;
+        e = run_dmma<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path, &remaining, scratch);
+        if (e == cudaSuccess && remaining > 0)
+            e = run_generic<T>(di, d, n, A, lda, in, out, nb, st, d - remaining, scratch, const_in);
         if (e != cudaErrorNotSupported) return e;
     }
     e = run_wspec5<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
@@ -321,7 +342,24 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
     e = run_pairtile<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches);
     if (e == cudaSuccess) t_last_path = "pairtile";
     if (e != cudaErrorNotSupported) return e;
-    return run_generic<T>(di, d, n, A, lda, in, out, nb, st);
+    return run_generic<T>(di, d, n, A, lda, in, out, nb, st, 0, scratch, const_in);
+}
+
+// 1 when the automatic dispatch sends (n, d) through a route that works in place through global memory
+template<typename T>
+static int needs_workspace(int d, int n)
+{
+    long long N = 1;
+    for (int i = 0; i < d; ++i)
+    {
+        N *= n;
+        if (N >= (1LL << 31)) return 1;
+    }
+    if (N * (long long)sizeof(T) <= 512) return 0;                 // tiny
+    if (n == 4 && d >= 4 && d <= 6) return 0;                      // regtile / wspec / wspec5
+    if (sizeof(T) == 8 && n == 8) return d > 4 ? 1 : 0;            // dmma
+    if (pairtile_fits<T>(d, n)) return 0;
+    return N > (long long)g_generic_resident_kib.load(std::memory_order_relaxed) * 1024 / (long long)sizeof(T) ? 1 : 0;
 }
 
 } // namespace kron
@@ -404,6 +442,40 @@ int kronmult_batched_f32_async(int d, int n, const float *const *A, int lda, flo
 {
     (void)ws;
     return (int)kron::dispatch<float>(d, n, A, lda, in, out, nb, static_cast<cudaStream_t>(stream));
+}
+
+int kronmult_batched_const_f64_async(int d, int n, const double *const *A, int lda, const double *const *in,
+                                     double **out, double **ws, int nb, void *stream)
+{
+    return (int)kron::dispatch<double>(d, n, A, lda, const_cast<double *const *>(in), out, nb,
+                                       static_cast<cudaStream_t>(stream), true, ws);
+}
+int kronmult_batched_const_f32_async(int d, int n, const float *const *A, int lda, const float *const *in, float **out,
+                                     float **ws, int nb, void *stream)
+{
+    return (int)kron::dispatch<float>(d, n, A, lda, const_cast<float *const *>(in), out, nb,
+                                      static_cast<cudaStream_t>(stream), true, ws);
+}
+int kronmult_batched_const_f64(int d, int n, const double *const *A, int lda, const double *const *in, double **out,
+                               double **ws, int nb)
+{
+    cudaError_t e = kron::dispatch<double>(d, n, A, lda, const_cast<double *const *>(in), out, nb, cudaStreamLegacy,
+                                           true, ws);
+    cudaError_t s = cudaDeviceSynchronize();
+    return (int)(e != cudaSuccess ? e : s);
+}
+int kronmult_batched_const_f32(int d, int n, const float *const *A, int lda, const float *const *in, float **out,
+                               float **ws, int nb)
+{
+    cudaError_t e = kron::dispatch<float>(d, n, A, lda, const_cast<float *const *>(in), out, nb, cudaStreamLegacy,
+                                          true, ws);
+    cudaError_t s = cudaDeviceSynchronize();
+    return (int)(e != cudaSuccess ? e : s);
+}
+int kronmult_b200_needs_workspace(int d, int n, int elem_size)
+{
+    if (d < 0 || n < 1 || (elem_size != 4 && elem_size != 8)) return -1;
+    return elem_size == 8 ? kron::needs_workspace<double>(d, n) : kron::needs_workspace<float>(d, n);
 }
 
 int kronmult_plan_create_f64(int d, int n, const double *const *A, int lda, double **in, double **out, int nb,

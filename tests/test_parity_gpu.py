@@ -326,3 +326,50 @@ def test_pairtile_ragged_and_misaligned(kron, oracle_mod, n, d, nb, dt):
         hp = batch.make_problem(d, n, nb, dt, "cpu", seed=nb + mis, alias="runs", items_per_output=3, lda=n + 3,
                                 misalign=mis).to_host()
         _check(kron, oracle_mod, hp, "pairtile")
+
+
+def _share_inputs(hp, n_unique):
+    """Items k and k' with k % n_unique == k' % n_unique read the SAME input vector (what an ASGarD-style caller
+    wants: out_i += K_ij x_j for many i per x_j).  Returns the shared problem and an expanded twin with one private
+    copy per item, which is what the reference's clobbering contract needs and what the oracle is run on."""
+    import copy
+    N = hp.N
+    shared = copy.copy(hp)
+    shared.in_off = hp.in_off[np.arange(hp.nb) % n_unique].copy()
+    twin = copy.copy(hp)
+    twin.in_slab = np.concatenate([hp.in_slab[o:o + N] for o in shared.in_off])
+    twin.in_off = np.arange(hp.nb, dtype=np.int64) * N
+    return shared, twin
+
+
+@pytest.mark.parametrize("n,d,nb", [(2, 2, 500), (4, 3, 300), (3, 5, 200), (4, 4, 200), (4, 5, 333), (4, 6, 40),
+                                    (6, 4, 60), (8, 4, 50), (5, 6, 10), (9, 4, 20), (10, 5, 6), (8, 5, 12), (8, 6, 5),
+                                    (7, 6, 4)])
+def test_read_only_shared_inputs(kron, oracle_mod, n, d, nb):
+    """kronmult_batched_const_*: inputs shared between items and left untouched, for every kernel family, including
+    the multi-pass routes that otherwise work in place in `input` (they get per-item scratch vectors)."""
+    for dt in (torch.float64, torch.float32):
+        hp = batch.make_problem(d, n, nb, dt, "cpu", seed=n * d, alias="runs", items_per_output=3, lda=n + 1).to_host()
+        shared, twin = _share_inputs(hp, max(1, nb // 4))
+        exp = oracle_mod.run(twin, "oracle", threads=1)
+        p = batch.from_host(shared, "cuda")
+        before = p.in_slab.clone()
+        A, i, o, _ = p.pointer_arrays()
+        w = None
+        if kron.needs_workspace(d, n, dt):
+            p.alloc_workspaces()
+            A, i, o, w = p.pointer_arrays()
+        kron.kronmult_batched_const(d, n, A, p.lda, i, o, w, nb, dtype=dt)
+        torch.cuda.synchronize()
+        err = oracle_mod.rel_l2(p.out_slab.cpu().numpy(), exp)
+        assert err <= _tol(hp), f"rel-L2 {err:.3e} (path {kron.last_path()})"
+        assert torch.equal(before, p.in_slab), f"input was modified (path {kron.last_path()})"
+
+
+def test_read_only_input_needs_workspace_for_multipass(kron):
+    """Without scratch vectors a shape that has to go through global memory is refused, not silently clobbered."""
+    assert kron.needs_workspace(6, 8, torch.float64) and not kron.needs_workspace(5, 4, torch.float64)
+    p = batch.make_problem(6, 8, 3, torch.float64, "cuda", seed=1)
+    A, i, o, _ = p.pointer_arrays()
+    with pytest.raises(kron.KronmultError):
+        kron.kronmult_batched_const(6, 8, A, p.lda, i, o, None, 3, dtype=torch.float64)
