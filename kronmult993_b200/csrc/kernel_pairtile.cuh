@@ -39,11 +39,19 @@ struct PairPick
     int minb, stages, acc, B, threads, fits;
 };
 
-template<typename T, int n, int d>
-struct PairCfg
+// Geometry shared by the resident kernel (a whole item per tile) and the pass kernel of the multi-pass route (a tile
+// of a longer vector): a tensor of DT indices of extent n, of which the GF slowest carry a factor and the Q = DT - GF
+// fastest are only along for the ride (contiguous rows of n^Q elements).
+template<typename T_, int n_, int DT_, int GF_>
+struct PairBase
 {
+    using T = T_;
+    static constexpr int n     = n_;
+    static constexpr int DT    = DT_;
+    static constexpr int GF    = GF_;
+    static constexpr int Q     = DT_ - GF_;
     static constexpr int S     = (int)sizeof(T);
-    static constexpr int N     = ipow(n, d);
+    static constexpr int N     = ipow(n, DT);
     static constexpr int NSQ   = n * n;
     static constexpr int TP    = N / NSQ; // tiles (= columns of every pass) per item
     static constexpr int VEC   = 16 / S;
@@ -53,20 +61,37 @@ struct PairCfg
     static constexpr int ITEM  = TP * BLK;
     static constexpr int ITEMP = (ITEM + VEC - 1) / VEC * VEC; // item pitch: 16-byte multiple
     static constexpr int RP    = (n + VEC - 1) / VEC * VEC;    // pitch of a factor column (column-major, as in global)
-    static constexpr int MAT   = d * n * RP;
+    static constexpr int MAT   = GF * n * RP;
     // factor pitch per stream: an odd number of 16-byte units, so that the broadcast column loads of lanes that
     // belong to different streams fall into different banks
     static constexpr int MATP  = ((MAT / VEC) % 2 == 0) ? MAT + VEC : MAT;
-    static constexpr int NPAIR = d / 2;
-    static constexpr int ODD   = d % 2;
+    static constexpr int NPAIR = GF / 2;
+    static constexpr int ODD   = GF % 2;
     static constexpr int NPASS = NPAIR + ODD;
     static constexpr int NCH   = N / VEC; // whole 16-byte chunks of a vector
     static constexpr int TAIL  = N % VEC;
+    static constexpr int LBQ   = ipow(n, Q); // contiguous row length of a tile of a longer vector
 
     // register tiles: rows are processed in HB blocks so that n^2 + n^2/HB values are live at a time
-    static constexpr int HB   = (S == 8) ? (n >= 7 ? 2 : 1) : (n >= 9 ? 2 : 1);
+    static constexpr int HB   = (S == 8) ? (n == 9 ? 3 : (n >= 7 ? 2 : 1)) : (n >= 9 ? 2 : 1);
     static constexpr int RB   = (n + HB - 1) / HB;
-    static constexpr int REGS = (NSQ + RB * n + n) * (S / 4) + 48; // estimate, checked against ptxas -v
+    // fp64 tiles of n >= 9 exceed the register file (2 n^2 live values): two threads share a tile, each producing
+    // CB of its n output columns (both read the whole tile: adjacent lanes, so the loads are broadcasts)
+    static constexpr int SPLIT = (S == 8 && n >= 9) ? 2 : 1;
+    static constexpr int CB    = (n + SPLIT - 1) / SPLIT;
+    static constexpr int TPS   = TP * SPLIT; // thread-tiles per item
+    static constexpr int REGS  = (SPLIT == 1 ? (NSQ + RB * n + n) * (S / 4) + 48 : 255); // estimate
+};
+
+template<typename T_, int n_, int d>
+struct PairCfg : PairBase<T_, n_, d, d>
+{
+    using Base = PairBase<T_, n_, d, d>;
+    using Base::S; using Base::ITEMP; using Base::MATP; using Base::TPS; using Base::REGS;
+    static constexpr bool TO_OUT   = true;   // the last pass accumulates into `output`
+    static constexpr bool REGFLUSH = d >= 3; // ... straight from registers (d = 2: one thread per item, via shared memory)
+    static constexpr int PSTRIDE   = d + 2;  // pointer slot layout per stream: d factors, input, output
+    static constexpr int POUT      = d + 1;
 
     static constexpr int PTRB = 3 * ((d + 2) * 8 + 4); // three slots of pointers + flag per stream
     static constexpr int bytes_item(int stages, int acc) { return (stages + acc) * ITEMP * S + stages * MATP * S + PTRB; }
@@ -101,9 +126,9 @@ struct PairCfg
                     if (bytes_item(1, 0) > budget) continue;
                 }
                 const int bmax = budget / bytes_item(stages, acc);
-                int B          = TP >= cap ? 1 : cap / TP;
+                int B          = TPS >= cap ? 1 : cap / TPS;
                 if (B > bmax) B = bmax;
-                const int tiles   = B * TP;
+                const int tiles   = B * TPS;
                 const int iters   = (tiles + cap - 1) / cap;
                 const int threads = ((tiles + iters - 1) / iters + 31) / 32 * 32;
                 int total         = minb * (tiles / iters);
@@ -124,7 +149,7 @@ struct PairCfg
     static constexpr bool FITS   = P.fits != 0;
     static constexpr int B       = P.B;
     static constexpr int THREADS = P.threads;
-    static constexpr int TILES   = B * TP;
+    static constexpr int TILES   = B * TPS; // thread-tiles per CTA step
 
     // byte offsets into dynamic shared memory
     static constexpr int OFF_ACC  = STAGES * B * ITEMP * S;
@@ -134,23 +159,36 @@ struct PairCfg
     static constexpr int SMEM     = OFF_FLAG + ((3 * B * 4 + 15) / 16) * 16;
 };
 
-template<typename T, int n, int d, int PASS>
+template<typename C_, int PASS>
 struct PairGeom
 {
-    using C = PairCfg<T, n, d>;
-    static constexpr bool SINGLE = (PASS == C::NPAIR); // the trailing single-factor pass of an odd d
+    using C = C_;
+    static constexpr int n = C::n;
+    static constexpr bool SINGLE = (PASS == C::NPAIR); // the trailing single-factor pass of an odd factor count
     static constexpr bool FINAL  = (PASS == C::NPASS - 1);
-    static constexpr int sB_log  = SINGLE ? ipow(n, d - 2) : ipow(n, 2 * PASS);
+    static constexpr int sB_log  = SINGLE ? ipow(n, C::DT - 2) : ipow(n, C::Q + 2 * PASS);
     static constexpr int sA_log  = sB_log * n;
     static constexpr int LO      = sB_log; // columns below the tile's two indices
     static constexpr int sH_log  = sA_log * n;
+    static constexpr bool CONTIG = !SINGLE && sB_log == 1; // the thread's tile is one contiguous block
     static constexpr int phys_stride(int x) { return x >= C::NSQ ? x / C::NSQ * C::BLK : x; }
     static constexpr int sB_ph = phys_stride(sB_log);
     static constexpr int sA_ph = phys_stride(sA_log);
     static constexpr int sH_ph = phys_stride(sH_log);
-    static constexpr int jb    = d - 1 - 2 * PASS; // faster factor of the pair (unused when SINGLE)
-    static constexpr int ja    = SINGLE ? 0 : d - 2 - 2 * PASS;
+    static constexpr int jb    = C::GF - 1 - 2 * PASS; // faster factor of the pair (unused when SINGLE)
+    static constexpr int ja    = SINGLE ? 0 : C::GF - 2 - 2 * PASS;
+    // results of the last pass leave through REDG straight from registers
+    static constexpr bool REGFLUSH = FINAL && C::TO_OUT && C::REGFLUSH;
 };
+
+// Offset in `output` of logical tile index i: rows of LBQ contiguous elements lie Lg apart in the long vector
+// (resident items: Q = 0 and the whole item is one tile -> the identity).
+template<typename C>
+__device__ __forceinline__ long long tile_goff(int i, long long Lg)
+{
+    if constexpr (C::DT == C::GF) return i;
+    else return (long long)(i / C::LBQ) * Lg + (i % C::LBQ);
+}
 
 // one column of a factor (column-major, pitch RP) as broadcast 128-bit loads
 template<typename T, int n, int RP>
@@ -181,14 +219,16 @@ __device__ __forceinline__ void load_col(const T *__restrict__ col, T (&m)[n])
 // `mats` = the item's d factors (column-major, pitch RP), `c` = column index in [0, TP), flag bits: 2 = first
 // item of a run of equal output pointers, 4 = last item of the run.
 // Both products run with the summation index k outermost: n * RB independent FMA chains advance together.
-template<typename T, int n, int d, int PASS>
-__device__ __forceinline__ void pair_tile(T *__restrict__ vec, T *__restrict__ acc, const T *__restrict__ mats,
-                                          int c, int flag, T *__restrict__ outp)
+template<typename C, int PASS>
+__device__ __forceinline__ void pair_tile(typename C::T *__restrict__ vec, typename C::T *__restrict__ acc,
+                                          const typename C::T *__restrict__ mats, int c, int flag,
+                                          typename C::T *__restrict__ outp, long long Lg)
 {
-    using C = PairCfg<T, n, d>;
-    using G = PairGeom<T, n, d, PASS>;
-    constexpr bool REGFLUSH = G::FINAL && d >= 3; // results leave through REDG straight from registers
-    constexpr bool CONTIG   = (PASS == 0 && !G::SINGLE); // the tile is one contiguous block
+    using T = typename C::T;
+    using G = PairGeom<C, PASS>;
+    constexpr int n         = C::n;
+    constexpr bool REGFLUSH = G::REGFLUSH;
+    constexpr bool CONTIG   = G::CONTIG;
     constexpr int RB        = C::RB;
 
     const int lo = (G::LO > 1) ? c % G::LO : 0;
@@ -197,6 +237,19 @@ __device__ __forceinline__ void pair_tile(T *__restrict__ vec, T *__restrict__ a
     if constexpr (C::PADE > 0 && G::LO > C::NSQ) base_ph += (lo / C::NSQ) * C::PADE;
     const int base_log = hi * G::sH_log + lo;
     T *__restrict__ x  = vec + base_ph;
+    // where the tile sits in `output` (REGFLUSH only): the tile's two indices lie above the contiguous rows
+    long long gbase = 0, gA = G::sA_log, gB = G::sB_log;
+    if constexpr (REGFLUSH)
+    {
+        gbase = tile_goff<C>(base_log, Lg);
+        if constexpr (C::DT != C::GF)
+        {
+            // an index at or above the contiguous rows moves by whole rows; the second index of a single-factor
+            // pass may lie inside the row
+            if constexpr (G::sA_log >= C::LBQ) gA = (long long)(G::sA_log / C::LBQ) * Lg;
+            if constexpr (G::sB_log >= C::LBQ) gB = (long long)(G::sB_log / C::LBQ) * Lg;
+        }
+    }
 
     // faster factor along the rows: Z[a][b'] = sum_k Mb(b', k) X[a][k]
     T Z[n][n];
@@ -288,9 +341,9 @@ __device__ __forceinline__ void pair_tile(T *__restrict__ vec, T *__restrict__ a
 #pragma unroll
                 for (int bp = 0; bp < n; ++bp)
                 {
-                    const int ph = base_ph + ap * G::sA_ph + bp * G::sB_ph;
-                    const int lg = base_log + ap * G::sA_log + bp * G::sB_log;
-                    T v          = Y[a][bp];
+                    const int ph       = base_ph + ap * G::sA_ph + bp * G::sB_ph;
+                    const long long lg = gbase + ap * gA + bp * gB;
+                    T v                = Y[a][bp];
                     if constexpr (C::ACC)
                     {
                         if (!(flag & 2)) v += acc[ph];
@@ -321,6 +374,112 @@ __device__ __forceinline__ void pair_tile(T *__restrict__ vec, T *__restrict__ a
     }
 }
 
+// The same for SPLIT = 2: this thread produces CB of the n output columns of the tile.  `half` is a
+// run-time value, so everything that depends on it is an address offset, never a register index.
+template<typename C, int PASS>
+__device__ __forceinline__ void pair_tile_split(typename C::T *__restrict__ vec, typename C::T *__restrict__ acc,
+                                                const typename C::T *__restrict__ mats, int c, int half, int flag,
+                                                typename C::T *__restrict__ outp, long long Lg)
+{
+    using T = typename C::T;
+    using G = PairGeom<C, PASS>;
+    constexpr int n         = C::n;
+    constexpr bool REGFLUSH = G::REGFLUSH;
+    constexpr int RB = C::RB, CB = C::CB;
+
+    const int lo = (G::LO > 1) ? c % G::LO : 0;
+    const int hi = (G::LO > 1) ? c / G::LO : c;
+    int base_ph  = hi * G::sH_ph + lo;
+    if constexpr (C::PADE > 0 && G::LO > C::NSQ) base_ph += (lo / C::NSQ) * C::PADE;
+    const int base_log = hi * G::sH_log + lo;
+    // odd n: the halves overlap in one column, which the second thread computes too but does not store
+    const int b0       = half * (n - CB);
+    const int skip     = half * (2 * CB - n);
+    long long gbase = 0, gA = G::sA_log, gB = G::sB_log;
+    if constexpr (REGFLUSH)
+    {
+        gbase = tile_goff<C>(base_log, Lg);
+        if constexpr (C::DT != C::GF)
+        {
+            // an index at or above the contiguous rows moves by whole rows; the second index of a single-factor
+            // pass may lie inside the row
+            if constexpr (G::sA_log >= C::LBQ) gA = (long long)(G::sA_log / C::LBQ) * Lg;
+            if constexpr (G::sB_log >= C::LBQ) gB = (long long)(G::sB_log / C::LBQ) * Lg;
+        }
+    }
+    T *__restrict__ x  = vec + base_ph;
+
+    T Z[n][CB];
+    if constexpr (!G::SINGLE)
+    {
+        const T *__restrict__ Mb = mats + G::jb * n * C::RP + b0;
+#pragma unroll
+        for (int k = 0; k < n; ++k)
+        {
+            T xc[n], m[CB];
+#pragma unroll
+            for (int a = 0; a < n; ++a) xc[a] = x[a * G::sA_ph + k * G::sB_ph];
+#pragma unroll
+            for (int j = 0; j < CB; ++j) m[j] = Mb[k * C::RP + j];
+#pragma unroll
+            for (int a = 0; a < n; ++a)
+#pragma unroll
+                for (int j = 0; j < CB; ++j) Z[a][j] = (k == 0) ? xc[a] * m[j] : fma(xc[a], m[j], Z[a][j]);
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int a = 0; a < n; ++a)
+#pragma unroll
+            for (int j = 0; j < CB; ++j) Z[a][j] = x[a * G::sA_ph + (b0 + j) * G::sB_ph];
+    }
+
+    const T *__restrict__ Ma = mats + G::ja * n * C::RP;
+#pragma unroll
+    for (int h = 0; h < C::HB; ++h)
+    {
+        const int a0 = h * RB;
+        T Y[RB][CB];
+#pragma unroll
+        for (int k = 0; k < n; ++k)
+        {
+            T m[n];
+            load_col<T, n, C::RP>(Ma + k * C::RP, m);
+#pragma unroll
+            for (int a = 0; a < RB; ++a)
+#pragma unroll
+                for (int j = 0; j < CB; ++j)
+                    if (a0 + a < n) Y[a][j] = (k == 0) ? Z[0][j] * m[a0 + a] : fma(Z[k][j], m[a0 + a], Y[a][j]);
+        }
+#pragma unroll
+        for (int a = 0; a < RB; ++a)
+        {
+            const int ap = a0 + a;
+            if (ap >= n) continue;
+#pragma unroll
+            for (int j = 0; j < CB; ++j)
+            {
+                if (j < skip) continue;
+                const int ph = base_ph + ap * G::sA_ph + (b0 + j) * G::sB_ph;
+                if constexpr (REGFLUSH)
+                {
+                    const long long lg = gbase + ap * gA + (b0 + j) * gB;
+                    T v                = Y[a][j];
+                    if constexpr (C::ACC)
+                    {
+                        if (!(flag & 2)) v += acc[ph];
+                        if (flag & 4) red_add(outp + lg, v);
+                        else acc[ph] = v;
+                    }
+                    else { red_add(outp + lg, v); }
+                }
+                else { vec[ph] = Y[a][j]; }
+            }
+        }
+    }
+}
+
 // Work distribution of the copy loops: groups of GL lanes (a power of two, or the whole CTA when there is a single
 // stream) walk the streams, f(b, gl, GL) then loops over the stream's PER_ITEM pieces from gl in steps of GL -- the
 // per-stream values (flag, pointers, alignment) are fetched once per stream and no division by PER_ITEM is needed.
@@ -337,28 +496,33 @@ __device__ __forceinline__ void for_items(int tid, F f)
     }
 }
 
-template<typename T, int n, int d, int PASS>
+template<typename C, int PASS>
 __device__ __forceinline__ void pair_passes(unsigned char *smem, int stage, const int *__restrict__ s_flag,
-                                            T *const *__restrict__ s_ptr)
+                                            typename C::T *const *__restrict__ s_ptr, long long Lg)
 {
-    using C = PairCfg<T, n, d>;
+    using T = typename C::T;
     T *vecs       = reinterpret_cast<T *>(smem) + (size_t)stage * C::B * C::ITEMP;
     T *accs       = reinterpret_cast<T *>(smem + C::OFF_ACC);
     const T *mats = reinterpret_cast<const T *>(smem + C::OFF_MAT) + (size_t)stage * C::B * C::MATP;
 #pragma unroll 1
     for (int tl = threadIdx.x; tl < C::TILES; tl += C::THREADS)
     {
-        const int b    = (C::B > 1) ? tl / C::TP : 0;
-        const int c    = (C::B > 1) ? tl - b * C::TP : tl;
+        const int tile = (C::SPLIT > 1) ? tl / C::SPLIT : tl;
+        const int b    = (C::B > 1) ? tile / C::TP : 0;
+        const int c    = (C::B > 1) ? tile - b * C::TP : tile;
         const int flag = s_flag[b];
-        if (flag)
-            pair_tile<T, n, d, PASS>(vecs + b * C::ITEMP, accs + b * C::ITEMP, mats + b * C::MATP, c, flag,
-                                     s_ptr[b * (d + 2) + d + 1]);
+        if (!flag) continue;
+        if constexpr (C::SPLIT > 1)
+            pair_tile_split<C, PASS>(vecs + b * C::ITEMP, accs + b * C::ITEMP, mats + b * C::MATP, c,
+                                     tl - tile * C::SPLIT, flag, s_ptr[b * C::PSTRIDE + C::POUT], Lg);
+        else
+            pair_tile<C, PASS>(vecs + b * C::ITEMP, accs + b * C::ITEMP, mats + b * C::MATP, c, flag,
+                               s_ptr[b * C::PSTRIDE + C::POUT], Lg);
     }
     if constexpr (PASS + 1 < C::NPASS)
     {
         __syncthreads();
-        pair_passes<T, n, d, PASS + 1>(smem, stage, s_flag, s_ptr);
+        pair_passes<C, PASS + 1>(smem, stage, s_flag, s_ptr, Lg);
     }
 }
 
@@ -506,7 +670,7 @@ __global__ void __launch_bounds__(PairCfg<T, n, d>::THREADS, PairCfg<T, n, d>::M
         if (t + 2 < L) fetch_ptrs(t + 2);
 
         const int *sf = slot_flag(t % 3);
-        pair_passes<T, n, d, 0>(smem, stage, sf, slot_ptrs(t % 3));
+        pair_passes<C, 0>(smem, stage, sf, slot_ptrs(t % 3), 0);
 
         if constexpr (d == 2)
         {
@@ -548,7 +712,7 @@ __global__ void __launch_bounds__(PairCfg<T, n, d>::THREADS, PairCfg<T, n, d>::M
 // host side
 // ----------------------------------------------------------------------------------------------
 template<typename T, int n, int d>
-constexpr bool pairtile_has() { return PairCfg<T, n, d>::FITS && !(sizeof(T) == 8 && n > 8); }
+constexpr bool pairtile_has() { return PairCfg<T, n, d>::FITS; }
 template<typename T>
 static bool pairtile_fits(int d, int n)
 {
@@ -569,7 +733,6 @@ static cudaError_t launch_pairtile(int sms, const T *const *A, int lda, T *const
                                    cudaStream_t st, std::atomic<long long> &launches)
 {
     using C = PairCfg<T, n, d>;
-    // fp64 tiles of n >= 9 do not fit the register file (2 n^2 live values)
     if constexpr (!pairtile_has<T, n, d>()) { return cudaErrorNotSupported; }
     else
     {

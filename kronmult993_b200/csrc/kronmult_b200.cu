@@ -17,6 +17,7 @@
 #include "kernel_wspec.cuh"
 #include "kernel_wspec5.cuh"
 #include "kernel_pairtile.cuh"
+#include "kernel_pairpass.cuh"
 
 #include <atomic>
 #include <mutex>
@@ -310,6 +311,11 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
     {
         e = run_pairtile<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches);
         if (e == cudaSuccess) t_last_path = "pairtile";
+        if (e == cudaErrorNotSupported && !(const_in && !scratch))
+        {
+            e = run_pairpass<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, scratch);
+            if (e == cudaSuccess) t_last_path = "pairtile-multipass";
+        }
         return e == cudaErrorNotSupported ? cudaErrorInvalidValue : e;
     }
     if (force == PATH_DMMA)
@@ -342,6 +348,12 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
     e = run_pairtile<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches);
     if (e == cudaSuccess) t_last_path = "pairtile";
     if (e != cudaErrorNotSupported) return e;
+    if (!(const_in && !scratch)) // works in place in `in` (or in the scratch vectors): refused below without either
+    {
+        e = run_pairpass<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, scratch);
+        if (e == cudaSuccess) t_last_path = "pairtile-multipass";
+        if (e != cudaErrorNotSupported) return e;
+    }
     return run_generic<T>(di, d, n, A, lda, in, out, nb, st, 0, scratch, const_in);
 }
 

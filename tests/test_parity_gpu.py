@@ -283,13 +283,13 @@ def test_blocking_entry_plans_shuffled_batches_once(kron, oracle_mod):
 
 
 def _pairtile_shapes(dt):
-    """(n, d) the pairtile family accepts: the vector (+ stage, + accumulator) fits in shared memory; fp64 tiles stop
-    at n = 8 (register file)."""
+    """(n, d) the pairtile family accepts: the vector (+ stage, + accumulator) fits in shared memory (fp64 tiles of
+    n = 9, 10 are shared by two threads)."""
     s = 8 if dt == torch.float64 else 4
     out = []
     for n in range(2, 11):
         for d in range(2, 7):
-            if n ** d * s <= 140 * 1024 and not (s == 8 and n > 8):
+            if n ** d * s <= 140 * 1024:
                 out.append((n, d))
     return out
 
@@ -373,3 +373,18 @@ def test_read_only_input_needs_workspace_for_multipass(kron):
     A, i, o, _ = p.pointer_arrays()
     with pytest.raises(kron.KronmultError):
         kron.kronmult_batched_const(6, 8, A, p.lda, i, o, None, 3, dtype=torch.float64)
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("n,d,nb", [(6, 6, 9), (7, 6, 5), (8, 5, 20), (8, 6, 4), (9, 5, 7), (9, 6, 3), (10, 5, 6),
+                                    (10, 6, 3)])
+def test_pairtile_multipass(kron, oracle_mod, n, d, nb, dt):
+    """Vectors beyond shared memory through the pairtile pass kernels (2 or 3 passes over global memory), forced:
+    runs of equal outputs, the reference's few-outputs pattern with lda = 67, ragged unit ranges, misaligned vectors."""
+    if n ** d * (8 if dt == torch.float64 else 4) <= 140 * 1024:
+        pytest.skip("fits in shared memory: resident kernel")
+    for alias, kw in (("runs", dict(items_per_output=3, lda=n + 1)), ("ref", dict(nb_distinct=2, matrices="reftest")),
+                      ("distinct", dict(misalign=1))):
+        hp = batch.make_problem(d, n, nb, dt, "cpu", seed=n * 11 + d, alias=alias, **kw).to_host()
+        _check(kron, oracle_mod, hp, "pairtile")
+        assert kron.last_path() == "pairtile-multipass"
