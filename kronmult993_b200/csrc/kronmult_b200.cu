@@ -331,6 +331,7 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
     // automatic: most specialised family first
     e = run_tiny<T>(d, n, A, lda, in, out, nb, st);
     if (e != cudaErrorNotSupported) return e;
+    if (!(n == 8 && d == 5)) // n = 8, d = 5: the pairtile pass kernels beat DMMA pass A + a generic single-factor pass (1.8x)
     {
         int remaining = 0;
         if (const_in && !scratch && sizeof(T) == 8 && n == 8 && d > 4) return cudaErrorInvalidValue;

@@ -381,7 +381,7 @@ def test_read_only_input_needs_workspace_for_multipass(kron):
 def test_pairtile_multipass(kron, oracle_mod, n, d, nb, dt):
     """Vectors beyond shared memory through the pairtile pass kernels (2 or 3 passes over global memory), forced:
     runs of equal outputs, the reference's few-outputs pattern with lda = 67, ragged unit ranges, misaligned vectors."""
-    if n ** d * (8 if dt == torch.float64 else 4) <= 140 * 1024:
+    if not kron.needs_workspace(d, n, dt):
         pytest.skip("fits in shared memory: resident kernel")
     for alias, kw in (("runs", dict(items_per_output=3, lda=n + 1)), ("ref", dict(nb_distinct=2, matrices="reftest")),
                       ("distinct", dict(misalign=1))):

@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--ref-gpu", action="store_true")
+    ap.add_argument("--path", default="auto", help="force a kernel family (api.PATHS)")
     ap.add_argument("--target-mb", type=float, default=0.0,
                     help="instead of the reference's batch size use a batch whose inputs total this many MB "
                          "(throughput rather than launch latency); aliasing then is runs of 32 items per output")
@@ -76,8 +77,14 @@ def main():
                                            matrices="reftest")
                 A, i, o, w = p.pointer_arrays()
                 torch.cuda.synchronize()
-                ms = time_call(lambda: api.kronmult_batched(d, n, A, p.lda, i, o, w, nb, dtype=dt, stream=stream),
-                               args.reps, stream)
+                api.force_path(args.path)
+                try:
+                    ms = time_call(lambda: api.kronmult_batched(d, n, A, p.lda, i, o, w, nb, dtype=dt, stream=stream),
+                                   args.reps, stream)
+                except api.KronmultError:
+                    api.force_path("auto")
+                    continue
+                api.force_path("auto")
                 fl, by = p.flops(), p.algorithmic_bytes()
                 roof = max(by / (hbm * 1e9), fl / peak)
                 line = {"n": n, "d": d, "level": level, "nb": nb, "N": n ** d, "path": api.last_path(),
