@@ -106,9 +106,9 @@ struct PairCfg : PairBase<T_, n_, d, d>
         tt = tt / 32 * 32;
         PairPick best{1, 1, 0, 1, 32, 0};
         int best_total = -1;
-        for (int minb = 8; minb >= 1; --minb)
+        for (int minb = 16; minb >= 1; --minb)
         {
-            if (minb == 7 || minb == 5) continue;
+            if (minb == 15 || minb == 14 || minb == 13 || minb == 11 || minb == 9 || minb == 7 || minb == 5) continue;
             const int budget = 227 * 1024 / minb - 1024 - 128; // the driver reserves 1 KiB per CTA
             int cap = (tt / minb) / 32 * 32;
             if (cap > 256) cap = 256;
@@ -133,6 +133,7 @@ struct PairCfg : PairBase<T_, n_, d, d>
                 const int threads = ((tiles + iters - 1) / iters + 31) / 32 * 32;
                 int total         = minb * (tiles / iters);
                 if (total > tt) total = tt;
+                if (threads <= 32) total += total / 4; // single-warp CTAs never wait for another warp at a barrier
                 if (total * 10 > best_total * 11) // fewer, fatter CTAs only for >10% more resident tiles
                 {
                     best_total = total;
@@ -329,7 +330,19 @@ __device__ __forceinline__ void pair_tile(typename C::T *__restrict__ vec, typen
             for (int a = 0; a < RB; ++a)
 #pragma unroll
                 for (int bp = 0; bp < n; ++bp)
-                    if (a0 + a < n) Y[a][bp] = (k == 0) ? Z[0][bp] * m[a0 + a] : fma(Z[k][bp], m[a0 + a], Y[a][bp]);
+                    if (a0 + a < n)
+                    {
+                        if (k == 0)
+                        {
+                            // inside a run of equal outputs the running sum is the addend of the first FMA: its
+                            // shared-memory load is issued ahead of the whole product instead of after it
+                            if (REGFLUSH && C::ACC && !(flag & 2))
+                                Y[a][bp] = fma(Z[0][bp], m[a0 + a], acc[base_ph + (a0 + a) * G::sA_ph + bp * G::sB_ph]);
+                            else
+                                Y[a][bp] = Z[0][bp] * m[a0 + a];
+                        }
+                        else Y[a][bp] = fma(Z[k][bp], m[a0 + a], Y[a][bp]);
+                    }
         }
 #pragma unroll
         for (int a = 0; a < RB; ++a)
@@ -346,7 +359,6 @@ __device__ __forceinline__ void pair_tile(typename C::T *__restrict__ vec, typen
                     T v                = Y[a][bp];
                     if constexpr (C::ACC)
                     {
-                        if (!(flag & 2)) v += acc[ph];
                         if (flag & 4) red_add(outp + lg, v);
                         else acc[ph] = v;
                     }
@@ -450,7 +462,17 @@ __device__ __forceinline__ void pair_tile_split(typename C::T *__restrict__ vec,
             for (int a = 0; a < RB; ++a)
 #pragma unroll
                 for (int j = 0; j < CB; ++j)
-                    if (a0 + a < n) Y[a][j] = (k == 0) ? Z[0][j] * m[a0 + a] : fma(Z[k][j], m[a0 + a], Y[a][j]);
+                    if (a0 + a < n)
+                    {
+                        if (k == 0)
+                        {
+                            if (REGFLUSH && C::ACC && !(flag & 2))
+                                Y[a][j] = fma(Z[0][j], m[a0 + a], acc[base_ph + (a0 + a) * G::sA_ph + (b0 + j) * G::sB_ph]);
+                            else
+                                Y[a][j] = Z[0][j] * m[a0 + a];
+                        }
+                        else Y[a][j] = fma(Z[k][j], m[a0 + a], Y[a][j]);
+                    }
         }
 #pragma unroll
         for (int a = 0; a < RB; ++a)
@@ -468,7 +490,6 @@ __device__ __forceinline__ void pair_tile_split(typename C::T *__restrict__ vec,
                     T v                = Y[a][j];
                     if constexpr (C::ACC)
                     {
-                        if (!(flag & 2)) v += acc[ph];
                         if (flag & 4) red_add(outp + lg, v);
                         else acc[ph] = v;
                     }

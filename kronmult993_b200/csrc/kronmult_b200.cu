@@ -28,6 +28,7 @@ namespace kron
 static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_force{PATH_AUTO};
 static std::atomic<int> g_generic_resident_kib{56}; // knob 3: largest vector (KiB) the generic path keeps resident
+static std::atomic<int> g_pairtile_resident_kib{227}; // knob 4: largest vector (KiB) the pairtile family keeps resident
 static thread_local const char *t_last_path = "none";
 
 struct DeviceInfo
@@ -346,7 +347,13 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
     if (e != cudaErrorNotSupported) return e;
     e = run_regtile<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
     if (e != cudaErrorNotSupported) return e;
-    e = run_pairtile<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches);
+    {
+        long long bytes = sizeof(T);
+        for (int i = 0; i < d && bytes < (1LL << 40); ++i) bytes *= n;
+        e = cudaErrorNotSupported;
+        if (bytes <= (long long)g_pairtile_resident_kib.load(std::memory_order_relaxed) * 1024)
+            e = run_pairtile<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches);
+    }
     if (e == cudaSuccess) t_last_path = "pairtile";
     if (e != cudaErrorNotSupported) return e;
     if (!(const_in && !scratch)) // works in place in `in` (or in the scratch vectors): refused below without either
@@ -534,6 +541,7 @@ int kronmult_b200_set_tuning(int knob, int value)
     if (knob == 1) { kron::g_autoplan.store(value); return 0; }
     if (knob == 2) { kron::g_wspec5_dbg.store(value); return 0; }
     if (knob == 3 && value >= 1 && value <= 220) { kron::g_generic_resident_kib.store(value); return 0; }
+    if (knob == 4 && value >= 0 && value <= 227) { kron::g_pairtile_resident_kib.store(value); return 0; }
     return (int)cudaErrorInvalidValue;
 }
 int kronmult_b200_force_path(int path)

@@ -9,7 +9,7 @@ cudaError_t run_pairpass<float>(int sms, int d, int n, const float *const *A, in
     switch (n)
     {
 #define KRON_PP(NN) case NN: return run_pairpass_n<float, NN>(sms, d, A, lda, in, out, nb, st, launches, scratch);
-        KRON_PP(6) KRON_PP(7) KRON_PP(8) KRON_PP(9) KRON_PP(10)
+        KRON_PP(5) KRON_PP(6) KRON_PP(7) KRON_PP(8) KRON_PP(9) KRON_PP(10)
 #undef KRON_PP
     default: return cudaErrorNotSupported;
     }

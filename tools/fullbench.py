@@ -44,6 +44,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--ref-gpu", action="store_true")
     ap.add_argument("--path", default="auto", help="force a kernel family (api.PATHS)")
+    ap.add_argument("--tune", default="", help="knob=value[,knob=value] for kronmult_b200_set_tuning")
     ap.add_argument("--target-mb", type=float, default=0.0,
                     help="instead of the reference's batch size use a batch whose inputs total this many MB "
                          "(throughput rather than launch latency); aliasing then is runs of 32 items per output")
@@ -58,6 +59,9 @@ def main():
         hbm = json.load(open(mp)).get("hbm_gbs", hbm)
     peak = (args.fp64_tflops if dt == torch.float64 else args.fp32_tflops) * 1e12
     torch.cuda.set_device(0)
+    for kv in [x for x in args.tune.split(",") if x]:
+        k, v = kv.split("=")
+        assert api.load_library().kronmult_b200_set_tuning(int(k), int(v)) == 0
     stream = torch.cuda.Stream()
     ref = None
     if args.ref_gpu:

@@ -43,6 +43,9 @@ def main():
     ap.add_argument("--plan", action="store_true", help="build an aliasing plan first and time its execution")
     ap.add_argument("--telemetry", action="store_true", help="NVML SM clock / power after every rep")
     ap.add_argument("--tune", default=None, help="knob=value[,knob=value] for kronmult_b200_set_tuning")
+    ap.add_argument("--share-inputs", action="store_true",
+                    help="ASGarD-style shared inputs through kronmult_batched_const: item t of output group i reads "
+                         "input vector (i + t) mod #outputs, so every vector is read by r items of r consecutive groups")
     args = ap.parse_args()
     hbm = 6552.3
     mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -67,7 +70,15 @@ def main():
         else:
             alias = args.alias or ("runs" if r > 1 else "distinct")
             p = batch.make_problem(d, n, nb, dt, "cuda", seed=993, alias=alias, items_per_output=r)
+        n_in = p.nb
+        if args.share_inputs and r != "ref" and r > 1:
+            k = torch.arange(p.nb, device="cuda")
+            n_in = p.n_outputs
+            p.in_off = ((k // r + k % r) % n_in) * p.N
         A, i, o, w = p.pointer_arrays()
+        if args.share_inputs and api.needs_workspace(p.d, p.n, dt):
+            p.alloc_workspaces()
+            A, i, o, w = p.pointer_arrays()
         api.force_path(args.path)
         torch.cuda.synchronize()  # the problem was built on the default stream
         times, tele = [], []
@@ -83,6 +94,8 @@ def main():
                 e0.record(stream)
                 if plan is not None:
                     plan.execute(stream)
+                elif args.share_inputs:
+                    api.kronmult_batched_const(p.d, p.n, A, p.lda, i, o, w, p.nb, dtype=dt, stream=stream)
                 else:
                     api.kronmult_batched(p.d, p.n, A, p.lda, i, o, w, p.nb, dtype=dt, stream=stream)
                 e1.record(stream)
@@ -95,9 +108,11 @@ def main():
         api.force_path("auto")
         t = min(times) * 1e-3
         fl, by = p.flops(), p.algorithmic_bytes()
+        if n_in != p.nb:  # every distinct input vector is compulsory traffic once
+            by -= (p.nb - n_in) * p.N * (8 if dt == torch.float64 else 4)
         peak = (args.fp64_tflops if dt == torch.float64 else args.fp32_tflops) * 1e12
         roof = max(by / (hbm * 1e9), fl / peak)
-        print(json.dumps({"config": name, "path": api.last_path(), "nb": nb, "ms": round(t * 1e3, 4),
+        print(json.dumps({"config": name + ("+shared_inputs" if n_in != p.nb else ""), "path": api.last_path(), "nb": nb, "ms": round(t * 1e3, 4),
                           "ms_all": [round(x, 4) for x in times], "gflops": round(fl / t * 1e-9, 1),
                           "alg_gbs": round(by / t * 1e-9, 1), "roofline_ms": round(roof * 1e3, 4),
                           "frac": round(roof / t, 4), "bound": "hbm" if by / (hbm * 1e9) >= fl / peak else "fp",
