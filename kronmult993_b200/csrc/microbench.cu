@@ -55,6 +55,36 @@ __global__ void __launch_bounds__(256) dmma_kernel(double *out, int iters)
     if (s == -12345.678) out[0] = s;
 }
 
+// DFMA and DMMA in ONE instruction stream: per trip 8 DMMA (8 x 256 MACs) and NF x 8 independent DFMA per thread.
+// If the FP64 tensor pipe and the FP64 FMA pipe are separate units the rates add up; if they share the datapath
+// the time is the sum of the two.
+template<int NF>
+__global__ void __launch_bounds__(256) mixed_kernel(double *out, int iters, double fa, double fb)
+{
+    double a = threadIdx.x * 1e-3, b = threadIdx.x * 2e-3;
+    double c[8][2], acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i][0] = c[i][1] = 0.0; acc[i] = threadIdx.x + i; }
+    for (int it = 0; it < iters; ++it)
+    {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+        {
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+#pragma unroll
+            for (int f = 0; f < NF; ++f) acc[(i + f) & 7] = acc[(i + f) & 7] * fa + fb;
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1] + acc[i];
+    if (s == -12345.678) out[0] = s;
+}
+
+template<int NF>
+static void mixed(const char *name, int sms, double *sink);
+
 __global__ void __launch_bounds__(256) read_kernel(const int4 *__restrict__ p, size_t n16, int *sink)
 {
     int acc = 0;
@@ -178,8 +208,32 @@ static void few_warps(const char *name, int sms, double *sink)
     CK(cudaFree(d_clk));
 }
 
+template<int NF>
+static void mixed(const char *name, int sms, double *sink)
+{
+    const int iters = 1 << 13, grid = sms * 8;
+    float ms = time_ms([&] { mixed_kernel<NF><<<grid, 256>>>(sink, iters, 1.0000001, 1e-9); });
+    const double warps = (double)grid * 8, trips = (double)iters * 8;
+    const double fl_mma = 2.0 * 256.0 * trips * warps, fl_fma = 2.0 * 32.0 * NF * trips * warps;
+    printf("{\"bench\": \"%s\", \"dfma_per_dmma\": %d, \"ms\": %.3f, \"tflops_dmma\": %.2f, \"tflops_dfma\": %.2f, \"tflops_total\": %.2f}\n",
+           name, NF, ms, fl_mma / ms * 1e-9, fl_fma / ms * 1e-9, (fl_mma + fl_fma) / ms * 1e-9);
+}
+
 int main(int argc, char **argv)
 {
+    if (argc > 1 && std::string(argv[1]) == "mixed")
+    {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, 0));
+        double *sink;
+        CK(cudaMalloc(&sink, 1024));
+        mixed<0>("dmma_dfma_mixed", prop.multiProcessorCount, sink);
+        mixed<2>("dmma_dfma_mixed", prop.multiProcessorCount, sink);
+        mixed<4>("dmma_dfma_mixed", prop.multiProcessorCount, sink);
+        mixed<8>("dmma_dfma_mixed", prop.multiProcessorCount, sink);
+        mixed<16>("dmma_dfma_mixed", prop.multiProcessorCount, sink);
+        return 0;
+    }
     if (argc > 1 && std::string(argv[1]) == "issue")
     {
         cudaDeviceProp prop;
