@@ -80,6 +80,7 @@ struct PairBase
     static constexpr int SPLIT = (S == 8 && n >= 9) ? 2 : 1;
     static constexpr int CB    = (n + SPLIT - 1) / SPLIT;
     static constexpr int TPS   = TP * SPLIT; // thread-tiles per item
+    static constexpr int KUNROLL = (n == 9 && DT_ == GF_) ? 1 : n; // split tiles: trips of the first product to unroll
     static constexpr int REGS  = (SPLIT == 1 ? (NSQ + RB * n + n) * (S / 4) + 48 : 255); // estimate
 };
 
@@ -426,6 +427,12 @@ __device__ __forceinline__ void pair_tile_split(typename C::T *__restrict__ vec,
     {
         const T *__restrict__ Mb = mats + G::jb * n * C::RP + b0;
 #pragma unroll
+        for (int a = 0; a < n; ++a)
+#pragma unroll
+            for (int j = 0; j < CB; ++j) Z[a][j] = T(0);
+        // k only moves addresses here, so the loop may stay rolled: for n = 9 ptxas otherwise hoists the loads of
+        // all trips (n^2 more live values) and spills; n = 10 fits and runs 7 % faster unrolled
+#pragma unroll(C::KUNROLL)
         for (int k = 0; k < n; ++k)
         {
             T xc[n], m[CB];
@@ -436,7 +443,7 @@ __device__ __forceinline__ void pair_tile_split(typename C::T *__restrict__ vec,
 #pragma unroll
             for (int a = 0; a < n; ++a)
 #pragma unroll
-                for (int j = 0; j < CB; ++j) Z[a][j] = (k == 0) ? xc[a] * m[j] : fma(xc[a], m[j], Z[a][j]);
+                for (int j = 0; j < CB; ++j) Z[a][j] = fma(xc[a], m[j], Z[a][j]);
         }
     }
     else

@@ -69,3 +69,22 @@ int main() {
         exe = os.path.join(td, "consumer")
         subprocess.run([nvcc, *build.ARCH, "--std=c++17", "-I", os.path.join(ROOT, "include"), f, "-o", exe,
                         "-L", os.path.dirname(build.LIB), "-lkronmult_b200"], check=True)
+
+
+def test_needs_workspace_query(kron):
+    """kronmult_b200_needs_workspace is host-only: 1 exactly for the shapes whose vector leaves shared memory."""
+    import torch
+
+    f64, f32 = torch.float64, torch.float32
+    assert not kron.needs_workspace(2, 2, f64)       # tiny
+    assert not kron.needs_workspace(5, 4, f64)       # wspec5
+    assert not kron.needs_workspace(4, 8, f64)       # dmma
+    assert not kron.needs_workspace(5, 6, f64)       # pairtile, 62 KiB
+    assert not kron.needs_workspace(6, 6, f32)       # pairtile, 182 KiB single stage
+    assert kron.needs_workspace(6, 6, f64)           # pairtile multi-pass
+    assert kron.needs_workspace(6, 8, f64) and kron.needs_workspace(5, 8, f64)
+    assert kron.needs_workspace(5, 10, f32) and kron.needs_workspace(6, 10, f64)
+    assert kron.needs_workspace(7, 11, f64)          # outside the envelope: generic multi-pass
+    assert not kron.needs_workspace(3, 11, f64)      # generic, resident
+    lib = kron.load_library()
+    assert lib.kronmult_b200_needs_workspace(3, 4, 2) == -1
