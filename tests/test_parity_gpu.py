@@ -388,3 +388,43 @@ def test_pairtile_multipass(kron, oracle_mod, n, d, nb, dt):
         hp = batch.make_problem(d, n, nb, dt, "cpu", seed=n * 11 + d, alias=alias, **kw).to_host()
         _check(kron, oracle_mod, hp, "pairtile")
         assert kron.last_path() == "pairtile-multipass"
+
+
+def _fuzz_cases(count, seed):
+    rng = np.random.default_rng(seed)
+    cases = []
+    while len(cases) < count:
+        n = int(rng.integers(2, 11))
+        d = int(rng.integers(1, 7))
+        N = n ** d
+        if N > 120000:
+            continue
+        nb = int(rng.integers(1, max(2, min(700, 300000 // N))))
+        alias = str(rng.choice(["runs", "distinct", "shuffled", "ref"]))
+        cases.append((n, d, nb, alias, int(rng.integers(1, 9)), int(rng.integers(0, 2)), int(rng.integers(0, 4)),
+                      bool(rng.integers(0, 2))))
+    return cases
+
+
+@pytest.mark.parametrize("n,d,nb,alias,r,mis,lda_extra,f32", _fuzz_cases(70, 20261017))
+def test_random_shapes_through_the_dispatcher(kron, oracle_mod, n, d, nb, alias, r, mis, lda_extra, f32):
+    """Seeded random (n, d, batch size, aliasing pattern, run length, alignment, leading dimension, type) through the
+    automatic dispatch, and the same problem through the read-only-input entry point with the inputs left untouched."""
+    dt = torch.float32 if f32 else torch.float64
+    kw = dict(items_per_output=r) if alias in ("runs", "shuffled") else (dict(nb_distinct=min(5, nb)) if alias == "ref" else {})
+    hp = batch.make_problem(d, n, nb, dt, "cpu", seed=n * 100 + d * 10 + nb, alias=alias, lda=n + lda_extra, misalign=mis,
+                            **kw).to_host()
+    exp = oracle_mod.run(hp, "oracle", threads=1)
+    _check(kron, oracle_mod, hp, expected=exp)
+    p = batch.from_host(hp, "cuda")
+    before = p.in_slab.clone()
+    A, i, o, w = p.pointer_arrays()
+    if kron.needs_workspace(d, n, dt):
+        p.alloc_workspaces()
+        A, i, o, w = p.pointer_arrays()
+    else:
+        w = None
+    kron.kronmult_batched_const(d, n, A, p.lda, i, o, w, nb, dtype=dt)
+    torch.cuda.synchronize()
+    assert oracle_mod.rel_l2(p.out_slab.cpu().numpy(), exp) <= _tol(hp), kron.last_path()
+    assert torch.equal(before, p.in_slab)
