@@ -16,7 +16,8 @@ MICROBENCH = os.path.join(_HERE, "kron_microbench")
 OBJ = os.path.join(_HERE, "_obj")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVCC_FLAGS = ["-O3", "--std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", *ARCH]
+NVCC_FLAGS = ["-O3", "--std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", *ARCH,
+              *os.environ.get("KRON_EXTRA_NVCC_FLAGS", "").split()]  # e.g. -DKRON_WSPEC5_EXPERIMENTS (ablation builds)
 
 
 def _nvcc() -> str:
