@@ -59,15 +59,82 @@ struct PairBase
     static constexpr int PADE  = (VECTILE && ((NSQ / VEC) % 2) == 0) ? VEC : 0;
     static constexpr int BLK   = NSQ + PADE;
     static constexpr int ITEM  = TP * BLK;
-    static constexpr int ITEMP = (ITEM + VEC - 1) / VEC * VEC; // item pitch: 16-byte multiple
+    static constexpr int NPAIR = GF / 2;
+    static constexpr int ODD   = GF % 2;
+    static constexpr int NPASS = NPAIR + ODD;
+
+    // Item pitch.  When an item has fewer than 32 tiles a warp spans several streams, and the pitch between them
+    // decides the bank conflicts of every pass: the first pass (one contiguous block per lane) likes the plain
+    // TP * BLK, the later ones (consecutive lanes on consecutive elements of one item, next item a pitch away) like
+    // a pitch that lets the items of a half-warp tile the banks.  A model of the shared-memory wavefronts (16-byte
+    // accesses by quarter-warps, 8-byte by half-warps, 4-byte by whole warps; equal addresses broadcast) picks the
+    // pad, at compile time.
+    static constexpr int wavefronts(const int (&addr)[32], int abytes) // addr in bytes, one access of abytes per lane
+    {
+        const int group = abytes == 16 ? 8 : (abytes == 8 ? 16 : 32);
+        int total = 0;
+        for (int g0 = 0; g0 < 32; g0 += group)
+        {
+            int cnt[32] = {};
+            int worst   = 0;
+            for (int l = g0; l < g0 + group; ++l)
+            {
+                if (addr[l] < 0) continue;
+                bool dup = false;
+                for (int m = g0; m < l; ++m) dup = dup || addr[m] == addr[l];
+                if (dup) continue;
+                const int bank = (addr[l] / abytes) % (128 / abytes);
+                if (++cnt[bank] > worst) worst = cnt[bank];
+            }
+            total += worst;
+        }
+        return total;
+    }
+    static constexpr long long pitch_cost(int pitch)
+    {
+        long long cost = 0;
+        int addr[32]   = {};
+        // first pass (Q = 0 only): lane tl = (b, c) owns block c of stream b
+        if (Q == 0)
+        {
+            for (int l = 0; l < 32; ++l) addr[l] = l < TP * 32 ? ((l / TP) * pitch + (l % TP) * BLK) * S : -1;
+            cost += (long long)wavefronts(addr, VECTILE ? 16 : S) * (VECTILE ? 2 * (NSQ / VEC) : 2 * NSQ);
+        }
+        // later passes: lane tl = (b, c), c = lo + LO * hi
+        for (int p = (Q == 0 ? 1 : 0); p < NPASS; ++p)
+        {
+            const bool single = (p == NPAIR);
+            const int sB      = single ? ipow(n, DT - 2) : ipow(n, Q + 2 * p);
+            const int sH      = sB * NSQ;
+            for (int l = 0; l < 32; ++l)
+            {
+                const int b = l / TP, c = l % TP;
+                const int lo = c % sB, hi = c / sB;
+                addr[l] = (b * pitch + lo + (lo / NSQ) * PADE + hi * (sH / NSQ) * BLK) * S;
+            }
+            cost += (long long)wavefronts(addr, S) * (2 * NSQ);
+        }
+        return cost;
+    }
+    static constexpr int pick_pitch()
+    {
+        const int base = (ITEM + VEC - 1) / VEC * VEC;
+        if (TP >= 32 || (S == 8 && n >= 9)) return base; // (split tiles follow another lane map: not modelled)
+        int best = base;
+        long long best_cost = pitch_cost(base);
+        for (int pad = VEC; pad <= 16 * (8 / S) * 2; pad += VEC)
+        {
+            const long long c = pitch_cost(base + pad);
+            if (c < best_cost) { best_cost = c; best = base + pad; }
+        }
+        return best;
+    }
+    static constexpr int ITEMP = pick_pitch(); // item pitch: a 16-byte multiple
     static constexpr int RP    = (n + VEC - 1) / VEC * VEC;    // pitch of a factor column (column-major, as in global)
     static constexpr int MAT   = GF * n * RP;
     // factor pitch per stream: an odd number of 16-byte units, so that the broadcast column loads of lanes that
     // belong to different streams fall into different banks
     static constexpr int MATP  = ((MAT / VEC) % 2 == 0) ? MAT + VEC : MAT;
-    static constexpr int NPAIR = GF / 2;
-    static constexpr int ODD   = GF % 2;
-    static constexpr int NPASS = NPAIR + ODD;
     static constexpr int NCH   = N / VEC; // whole 16-byte chunks of a vector
     static constexpr int TAIL  = N % VEC;
     static constexpr int LBQ   = ipow(n, Q); // contiguous row length of a tile of a longer vector
