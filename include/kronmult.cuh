@@ -35,3 +35,15 @@ __host__ cudaError kronmult_batched(int const matrix_count, int const matrix_siz
                                     T const *const matrix_list_batched[], int const matrix_stride,
                                     T *input_batched[], T *output_batched[], T *workspace_batched[],
                                     int const nb_batch);
+
+// ---- extension (not in the reference): read-only, shareable inputs -------------------------------------------------
+// Same operation, but input_batched[k] is NEVER written, so entries may repeat (an ASGarD-style caller keeps one copy
+// of every x_j instead of one per batch item, kronmult_gpu/kronmult.cuh:23 / README.md:49 force the copies today).
+// workspace_batched[k] must be a distinct n^d-element scratch vector per item when
+// kronmult_b200_needs_workspace(matrix_count, matrix_size, sizeof(T)) (include/kronmult_b200.h) returns 1, and may be
+// nullptr otherwise.  float and double only; blocking like kronmult_batched.
+template<typename T>
+__host__ cudaError kronmult_batched_const(int const matrix_count, int const matrix_size,
+                                          T const *const matrix_list_batched[], int const matrix_stride,
+                                          T const *const input_batched[], T *output_batched[],
+                                          T *workspace_batched[], int const nb_batch);

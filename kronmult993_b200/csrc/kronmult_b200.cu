@@ -578,3 +578,25 @@ __host__ cudaError kronmult_batched<float>(int const matrix_count, int const mat
                                                        matrix_stride, input_batched, output_batched,
                                                        workspace_batched, nb_batch));
 }
+
+template<>
+__host__ cudaError kronmult_batched_const<double>(int const matrix_count, int const matrix_size,
+                                                  double const *const matrix_list_batched[], int const matrix_stride,
+                                                  double const *const input_batched[], double *output_batched[],
+                                                  double *workspace_batched[], int const nb_batch)
+{
+    return static_cast<cudaError>(kronmult_batched_const_f64(matrix_count, matrix_size, matrix_list_batched,
+                                                             matrix_stride, input_batched, output_batched,
+                                                             workspace_batched, nb_batch));
+}
+
+template<>
+__host__ cudaError kronmult_batched_const<float>(int const matrix_count, int const matrix_size,
+                                                 float const *const matrix_list_batched[], int const matrix_stride,
+                                                 float const *const input_batched[], float *output_batched[],
+                                                 float *workspace_batched[], int const nb_batch)
+{
+    return static_cast<cudaError>(kronmult_batched_const_f32(matrix_count, matrix_size, matrix_list_batched,
+                                                             matrix_stride, input_batched, output_batched,
+                                                             workspace_batched, nb_batch));
+}
