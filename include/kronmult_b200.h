@@ -114,7 +114,9 @@ int kronmult_b200_force_path(int path);
  *         1: implicit planning in the blocking entry points (1 = on, default; 0 = off).
  *         2: ablation variants of the n=4, d=5 kernel (only in builds with -DKRON_WSPEC5_EXPERIMENTS).
  *         3: largest vector, in KiB, that the shape-agnostic path keeps resident in shared memory in one pass
- *            (default 56); longer vectors take the tiled multi-pass route, which works in place in `in`. */
+ *            (default 56); longer vectors take the tiled multi-pass route, which works in place in `in`.
+ *         4: largest vector, in KiB, that the pairtile family keeps resident (default 227 = whatever fits); smaller
+ *            values send long vectors through the pairtile multi-pass route (development: resident measured faster). */
 int kronmult_b200_set_tuning(int knob, int value);
 
 #ifdef __cplusplus
