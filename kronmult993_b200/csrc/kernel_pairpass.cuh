@@ -34,6 +34,7 @@ struct PassCfg : PairBase<T_, n_, GF_ + Q_, GF_>
     static constexpr int STAGES    = 2;
     static constexpr int ACC       = FINAL_ ? 1 : 0;
     static constexpr int TILES     = TPS;
+    static constexpr int LANEMAP   = 0;
     static constexpr int cap()
     {
         int c = (65536 / REGS) / 32 * 32;

@@ -100,7 +100,13 @@ struct PairBase
             for (int l = 0; l < 32; ++l) addr[l] = l < TP * 32 ? ((l / TP) * pitch + (l % TP) * BLK) * S : -1;
             cost += (long long)wavefronts(addr, VECTILE ? 16 : S) * (VECTILE ? 2 * (NSQ / VEC) : 2 * NSQ);
         }
-        // later passes: lane tl = (b, c), c = lo + LO * hi
+        return cost + later_cost(pitch, 32, 0);
+    }
+    // later passes: lane tl = (b, c), c = lo + LO * hi; lanemap 0: c fastest (b = tl / TP), 1: b fastest (b = tl % B)
+    static constexpr long long later_cost(int pitch, int B, int lanemap)
+    {
+        long long cost = 0;
+        int addr[32]   = {};
         for (int p = (Q == 0 ? 1 : 0); p < NPASS; ++p)
         {
             const bool single = (p == NPAIR);
@@ -108,9 +114,9 @@ struct PairBase
             const int sH      = sB * NSQ;
             for (int l = 0; l < 32; ++l)
             {
-                const int b = l / TP, c = l % TP;
+                const int b = lanemap ? l % B : l / TP, c = lanemap ? l / B : l % TP;
                 const int lo = c % sB, hi = c / sB;
-                addr[l] = (b * pitch + lo + (lo / NSQ) * PADE + hi * (sH / NSQ) * BLK) * S;
+                addr[l] = (b < B && c < TP) ? (b * pitch + lo + (lo / NSQ) * PADE + hi * (sH / NSQ) * BLK) * S : -1;
             }
             cost += (long long)wavefronts(addr, S) * (2 * NSQ);
         }
@@ -219,6 +225,10 @@ struct PairCfg : PairBase<T_, n_, d, d>
     static constexpr int B       = P.B;
     static constexpr int THREADS = P.threads;
     static constexpr int TILES   = B * TPS; // thread-tiles per CTA step
+    // lane -> (stream, column) map of every pass but the first: streams fastest when the wavefront model of
+    // PairBase says so for this pitch and stream count (e.g. n = 6, d = 3 fp64: 2 wavefronts per access instead of 4)
+    static constexpr int LANEMAP = (B > 1 && Base::SPLIT == 1 && Base::TP < 32
+                                    && Base::later_cost(ITEMP, B, 1) < Base::later_cost(ITEMP, B, 0)) ? 1 : 0;
 
     // byte offsets into dynamic shared memory
     static constexpr int OFF_ACC  = STAGES * B * ITEMP * S;
@@ -603,8 +613,9 @@ __device__ __forceinline__ void pair_passes(unsigned char *smem, int stage, cons
     for (int tl = threadIdx.x; tl < C::TILES; tl += C::THREADS)
     {
         const int tile = (C::SPLIT > 1) ? tl / C::SPLIT : tl;
-        const int b    = (C::B > 1) ? tile / C::TP : 0;
-        const int c    = (C::B > 1) ? tile - b * C::TP : tile;
+        constexpr bool BFAST = C::LANEMAP == 1 && !PairGeom<C, PASS>::CONTIG;
+        const int b    = (C::B > 1) ? (BFAST ? tile % C::B : tile / C::TP) : 0;
+        const int c    = (C::B > 1) ? (BFAST ? tile / C::B : tile - b * C::TP) : tile;
         const int flag = s_flag[b];
         if (!flag) continue;
         if constexpr (C::SPLIT > 1)
