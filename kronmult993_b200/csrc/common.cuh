@@ -10,8 +10,8 @@ namespace kron
 enum Path : int
 {
     PATH_AUTO    = 0,
-    PATH_GENERIC = 1, // shared-memory tiles, runtime d, any n <= 32, multi-pass for large n^d
-    PATH_TINY    = 2, // one thread per item, everything in registers (n^d <= 16)
+    PATH_GENERIC = 1, // shared-memory tiles, runtime d, any n <= 32, multi-pass for large n^d (fallback beyond n = 10, d = 6)
+    PATH_TINY    = 2, // one thread per item, everything in registers (n^d * sizeof(T) <= 512 bytes)
     PATH_REGTILE = 3, // register-tiled in-place mode products, compile-time (n,d), n in {3,4,5,6}
     PATH_DMMA    = 4, // n = 8 on the FP64 tensor pipe (mma.sync m8n8k4), double only
     PATH_WSPEC   = 5, // n = 4, d = 5,6: warp-specialised two-phase kernel with 64-value register tiles
