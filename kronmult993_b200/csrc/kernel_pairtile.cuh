@@ -125,7 +125,7 @@ struct PairBase
     static constexpr int pick_pitch()
     {
         const int base = (ITEM + VEC - 1) / VEC * VEC;
-        if (TP >= 32 || (S == 8 && n >= 9)) return base; // (split tiles follow another lane map: not modelled)
+        if (TP >= 32 || n >= 9) return base; // (split tiles follow another lane map: not modelled)
         int best = base;
         long long best_cost = pitch_cost(base);
         for (int pad = VEC; pad <= 16 * (8 / S) * 2; pad += VEC)
@@ -146,15 +146,16 @@ struct PairBase
     static constexpr int LBQ   = ipow(n, Q); // contiguous row length of a tile of a longer vector
 
     // register tiles: rows are processed in HB blocks so that n^2 + n^2/HB values are live at a time
-    static constexpr int HB   = (S == 8) ? (n == 9 ? 3 : (n >= 7 ? 2 : 1)) : (n >= 9 ? 2 : 1);
+    static constexpr int HB   = (S == 8) ? (n == 9 ? 3 : (n >= 7 ? 2 : 1)) : 1;
     static constexpr int RB   = (n + HB - 1) / HB;
-    // fp64 tiles of n >= 9 exceed the register file (2 n^2 live values): two threads share a tile, each producing
-    // CB of its n output columns (both read the whole tile: adjacent lanes, so the loads are broadcasts)
-    static constexpr int SPLIT = (S == 8 && n >= 9) ? 2 : 1;
+    // tiles of n >= 9 exceed the register file in fp64 (2 n^2 live values) and leave too few warps in fp32: two threads
+    // share a tile, each producing CB of its n output columns (both read the whole tile: adjacent lanes, so the loads
+    // are broadcasts)
+    static constexpr int SPLIT = (n >= 9) ? 2 : 1;
     static constexpr int CB    = (n + SPLIT - 1) / SPLIT;
     static constexpr int TPS   = TP * SPLIT; // thread-tiles per item
     static constexpr int KUNROLL = (n == 9 && DT_ == GF_) ? 1 : n; // split tiles: trips of the first product to unroll
-    static constexpr int REGS  = (SPLIT == 1 ? (NSQ + RB * n + n) * (S / 4) + 48 : 255); // estimate
+    static constexpr int REGS  = (SPLIT == 1 ? (NSQ + RB * n + n) * (S / 4) + 48 : (S == 8 ? 255 : 168)); // estimate
 };
 
 template<typename T_, int n_, int d>
