@@ -125,7 +125,7 @@ struct PairBase
     static constexpr int pick_pitch()
     {
         const int base = (ITEM + VEC - 1) / VEC * VEC;
-        if (TP >= 32 || n >= 9) return base; // (split tiles follow another lane map: not modelled)
+        if (TP >= 32 || SPLIT > 1) return base; // (split tiles follow another lane map: not modelled)
         int best = base;
         long long best_cost = pitch_cost(base);
         for (int pad = VEC; pad <= 16 * (8 / S) * 2; pad += VEC)
@@ -151,7 +151,9 @@ struct PairBase
     // tiles of n >= 9 exceed the register file in fp64 (2 n^2 live values) and leave too few warps in fp32: two threads
     // share a tile, each producing CB of its n output columns (both read the whole tile: adjacent lanes, so the loads
     // are broadcasts)
-    static constexpr int SPLIT = (n >= 9) ? 2 : 1;
+    // (also fp32 n = 8, d = 4: 64 tiles per item -> 128 threads per CTA instead of 64; measured 1.42x, the other n = 7, 8
+    // shapes lose 1-22 % with split tiles)
+    static constexpr int SPLIT = (n >= 9 || (S == 4 && n == 8 && DT_ == 4 && GF_ == 4)) ? 2 : 1;
     static constexpr int CB    = (n + SPLIT - 1) / SPLIT;
     static constexpr int TPS   = TP * SPLIT; // thread-tiles per item
     static constexpr int KUNROLL = (n == 9 && DT_ == GF_) ? 1 : n; // split tiles: trips of the first product to unroll
