@@ -256,7 +256,7 @@ static cudaError_t run_tiny(int d, int n, const T *const *A, int lda, T *const *
     if (n == NN && d == DD) return launch_tiny<T, NN, DD>(A, lda, in, out, nb, st);
     KRON_TINY(2, 1) KRON_TINY(2, 2) KRON_TINY(2, 3) KRON_TINY(2, 4) KRON_TINY(2, 5) KRON_TINY(2, 6)
     KRON_TINY(3, 1) KRON_TINY(3, 2) KRON_TINY(3, 3)
-    if constexpr (sizeof(T) == 8) { KRON_TINY(3, 4) } // 81 doubles + one 3x3 factor: 162 + 18 registers
+    if constexpr (sizeof(T) == 8) { KRON_TINY(3, 4) KRON_TINY(7, 2) } // 81 doubles + a 3x3 factor / 49 + a 7x7 factor
     KRON_TINY(4, 1) KRON_TINY(4, 2) KRON_TINY(4, 3)
     KRON_TINY(5, 1) KRON_TINY(6, 1) KRON_TINY(7, 1) KRON_TINY(8, 1) KRON_TINY(9, 1) KRON_TINY(10, 1)
     KRON_TINY(5, 2) KRON_TINY(6, 2)
