@@ -152,8 +152,9 @@ struct PairBase
     // share a tile, each producing CB of its n output columns (both read the whole tile: adjacent lanes, so the loads
     // are broadcasts)
     // (also fp32 n = 8, d = 4: 64 tiles per item -> 128 threads per CTA instead of 64; measured 1.42x, the other n = 7, 8
-    // shapes lose 1-22 % with split tiles; and fp64 n = 8, d = 2: one tile per item, two threads per item, 1.13x)
-    static constexpr int SPLIT = (n >= 9 || (S == 4 && n == 8 && DT_ == 4 && GF_ == 4) || (S == 8 && n == 8 && DT_ == 2)) ? 2 : 1;
+    // shapes lose 1-22 % with split tiles; and fp64 n = 8: d = 2 1.13x, d = 3 1.50x, multi-pass d = 5 1.13x;
+    // fp64 n = 7 is a wash: d = 3, 5 +6 %, d = 4, 6 -15 %)
+    static constexpr int SPLIT = (n >= 9 || (S == 4 && n == 8 && DT_ == 4 && GF_ == 4) || (S == 8 && n == 8)) ? 2 : 1;
     static constexpr int CB    = (n + SPLIT - 1) / SPLIT;
     static constexpr int TPS   = TP * SPLIT; // thread-tiles per item
     static constexpr int KUNROLL = (n == 9 && DT_ == GF_) ? 1 : n; // split tiles: trips of the first product to unroll
