@@ -80,6 +80,54 @@ int kronmult_batched_host_f32(int d, int n, const float *const *A, int lda, floa
 int kronmult_partition_by_output(const void *const *out, int nb, int n_ranks, long long split_threshold,
                                  int *owner, unsigned char *needs_reduce);
 
+/* Multi-GPU execution of one rank's shard, with the ONE collective of the design (no reference counterpart;
+ * BASELINE.json north_star).  One process per GPU.  A kronmult_comm wraps an NCCL communicator over the ranks
+ * (NCCL is loaded lazily with dlopen: the single-GPU entry points have no NCCL dependency):
+ *   kronmult_comm_unique_id   rank 0 obtains the 128-byte ncclUniqueId and hands it to the other ranks by any
+ *                             means (bench.py / the tests broadcast it with torch.distributed);
+ *   kronmult_comm_create      collective over all ranks (ncclCommInitRank on the CURRENT device);
+ *   kronmult_comm_adopt       wrap a communicator the caller already has (ncclComm_t; not destroyed by _destroy);
+ *   kronmult_comm_destroy.
+ * kronmult_batched_sharded_*: like kronmult_batched_*_async on this rank's items (A, in, out, nb as above), plus
+ * `shared_out`: HOST array of n_shared DEVICE pointers = this rank's own copies of the output vectors whose items
+ * were split across ranks (needs_reduce of kronmult_partition_by_output) -- the same vectors in the same order on
+ * every rank -- and `owner` (HOST array, n_shared ranks, or NULL).  Items that write a shared vector accumulate
+ * into zero-initialised scratch; the scratch is summed over all ranks with ONE ncclAllReduce over NVLink and the
+ * total is added into this rank's copy of every shared vector with owner[j] == rank (NULL: into every rank's copy).
+ * Every rank must make the call (also with nb = 0).  Stream-ordered; returns cudaErrorNotSupported if more than one
+ * rank is asked for and libnccl.so.2 cannot be loaded.
+ * kronmult_comm_last_collective_ms: device time of the most recent all-reduce (cudaEvents on the stream; waits for
+ * it) and the number of collectives issued so far. */
+typedef struct kronmult_comm kronmult_comm;
+int kronmult_comm_unique_id(void *id128);
+int kronmult_comm_create(const void *id128, int world, int rank, kronmult_comm **comm);
+int kronmult_comm_adopt(void *nccl_comm, int world, int rank, kronmult_comm **comm);
+int kronmult_comm_destroy(kronmult_comm *comm);
+int kronmult_comm_last_collective_ms(kronmult_comm *comm, float *ms, long long *count);
+int kronmult_batched_sharded_f64(int d, int n, const double *const *A, int lda, double **in, double **out, double **ws,
+                                 int nb, double *const *shared_out, int n_shared, const int *owner, kronmult_comm *comm,
+                                 void *stream);
+int kronmult_batched_sharded_f32(int d, int n, const float *const *A, int lda, float **in, float **out, float **ws,
+                                 int nb, float *const *shared_out, int n_shared, const int *owner, kronmult_comm *comm,
+                                 void *stream);
+
+/* Device-side batch builder for ASGarD-style callers (no reference counterpart; SURVEY.md section 8(f) rank 3: the
+ * reference's harness fills the pointer arrays on the host, tests/utils/utils_gpu.h:58-65; the batch shape is
+ * ASGarD's, tests/utils/batch_size.h:16-20).  Builds the pointer arrays of the batch
+ *     { (i, j, t) : row element i in [row0,row1), column element j in [col0,col1), term t in [0,nterms) }
+ * ordered (i, j, t) so that equal output pointers are consecutive:
+ *     A[k*d + dim] = coeff[t*d + dim] + n*cells[i*d+dim] + n*cells[j*d+dim]*lda    (an n x n window, nothing copied)
+ *     in[k] = x + j*n^d  (shared by rows and terms -> call kronmult_batched_const_*),   out[k] = y + i*n^d.
+ * cells: DEVICE array [num_elements*d] of 1-D cell indices; coeff: DEVICE array [nterms*d] of DEVICE pointers to the
+ * one-dimensional coefficient matrices (column-major, leading dimension lda); A / in / out: DEVICE arrays of
+ * nb*d / nb / nb pointers with nb = (row1-row0)*(col1-col0)*nterms (also returned in *nb).  Stream-ordered. */
+int kronmult_build_batch_f64(int d, int n, int lda, const int *cells, const double *const *coeff, int nterms, int row0,
+                             int row1, int col0, int col1, const double *x, double *y, const double **A,
+                             const double **in, double **out, long long *nb, void *stream);
+int kronmult_build_batch_f32(int d, int n, int lda, const int *cells, const float *const *coeff, int nterms, int row0,
+                             int row1, int col0, int col1, const float *x, float *y, const float **A, const float **in,
+                             float **out, long long *nb, void *stream);
+
 /* Batch / aliasing planner (no reference counterpart; BASELINE.json north_star).  Every kernel sums runs of
  * consecutive items that share an output pointer on chip; a plan sorts the batch by output pointer on the
  * device (stable, so equal pointers keep their batch order) and keeps sorted copies of the three pointer
@@ -107,7 +155,7 @@ const char *kronmult_b200_version(void);
 long long kronmult_b200_launch_count(void);
 /* name of the kernel family chosen by the most recent call on this thread ("tiny", "generic", ...) */
 const char *kronmult_b200_last_path(void);
-/* 0 = automatic dispatch; otherwise force a kernel family (see kronmult993_b200/csrc/dispatch.h).
+/* 0 = automatic dispatch; otherwise force a kernel family (the kron::Path codes in kronmult993_b200/csrc/common.cuh).
  * Unsupported combinations make the next call return cudaErrorInvalidValue.  For tests. */
 int kronmult_b200_force_path(int path);
 /* knobs.  0: regtile operand staging (0 = TMA into shared memory, 1 = L1 prefetch; development).
@@ -116,7 +164,8 @@ int kronmult_b200_force_path(int path);
  *         3: largest vector, in KiB, that the shape-agnostic path keeps resident in shared memory in one pass
  *            (default 56); longer vectors take the tiled multi-pass route, which works in place in `in`.
  *         4: largest vector, in KiB, that the pairtile family keeps resident (default 227 = whatever fits); smaller
- *            values send long vectors through the pairtile multi-pass route (development: resident measured faster). */
+ *            values send long vectors through the pairtile multi-pass route (development: resident measured faster).
+ *         5: variant of the n=4, d=5 kernel (development; only in builds with -DKRON_SYM5_VARIANTS). */
 int kronmult_b200_set_tuning(int knob, int value);
 
 #ifdef __cplusplus

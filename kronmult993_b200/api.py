@@ -22,9 +22,9 @@ import torch
 
 from . import build as _build
 
-PATH_AUTO, PATH_GENERIC, PATH_TINY, PATH_REGTILE, PATH_DMMA, PATH_WSPEC, PATH_WSPEC5, PATH_PAIRTILE = 0, 1, 2, 3, 4, 5, 6, 7
+PATH_AUTO, PATH_GENERIC, PATH_TINY, PATH_REGTILE, PATH_DMMA, PATH_WSPEC, PATH_WSPEC5, PATH_PAIRTILE, PATH_SYM5 = 0, 1, 2, 3, 4, 5, 6, 7, 8
 PATHS = {"auto": PATH_AUTO, "generic": PATH_GENERIC, "tiny": PATH_TINY, "regtile": PATH_REGTILE, "dmma": PATH_DMMA,
-         "wspec": PATH_WSPEC, "wspec5": PATH_WSPEC5, "pairtile": PATH_PAIRTILE}
+         "wspec": PATH_WSPEC, "wspec5": PATH_WSPEC5, "pairtile": PATH_PAIRTILE, "sym5": PATH_SYM5}
 
 # every symbol include/kronmult_b200.h declares (tests/test_abi.py checks the header against this)
 C_SYMBOLS = (
@@ -36,6 +36,15 @@ C_SYMBOLS = (
     "kronmult_batched_host_f64",
     "kronmult_batched_host_f32",
     "kronmult_partition_by_output",
+    "kronmult_comm_unique_id",
+    "kronmult_comm_create",
+    "kronmult_comm_adopt",
+    "kronmult_comm_destroy",
+    "kronmult_comm_last_collective_ms",
+    "kronmult_batched_sharded_f64",
+    "kronmult_batched_sharded_f32",
+    "kronmult_build_batch_f64",
+    "kronmult_build_batch_f32",
     "kronmult_plan_create_f64",
     "kronmult_plan_create_f32",
     "kronmult_batched_const_f64",
@@ -107,6 +116,24 @@ def load_library() -> ctypes.CDLL:
         f.restype, f.argtypes = c_int, [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int]
         f = getattr(lib, f"kronmult_batched_const_{sfx}_async")
         f.restype, f.argtypes = c_int, [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp]
+    for sfx in ("f64", "f32"):
+        f = getattr(lib, f"kronmult_batched_sharded_{sfx}")
+        f.restype = c_int
+        f.argtypes = [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp]
+    for sfx in ("f64", "f32"):
+        f = getattr(lib, f"kronmult_build_batch_{sfx}")
+        f.restype = c_int
+        f.argtypes = [c_int, c_int, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
+                      ctypes.POINTER(ctypes.c_longlong), c_vp]
+    lib.kronmult_comm_unique_id.restype, lib.kronmult_comm_unique_id.argtypes = c_int, [c_vp]
+    lib.kronmult_comm_create.restype = c_int
+    lib.kronmult_comm_create.argtypes = [c_vp, c_int, c_int, ctypes.POINTER(c_vp)]
+    lib.kronmult_comm_adopt.restype = c_int
+    lib.kronmult_comm_adopt.argtypes = [c_vp, c_int, c_int, ctypes.POINTER(c_vp)]
+    lib.kronmult_comm_destroy.restype, lib.kronmult_comm_destroy.argtypes = c_int, [c_vp]
+    lib.kronmult_comm_last_collective_ms.restype = c_int
+    lib.kronmult_comm_last_collective_ms.argtypes = [c_vp, ctypes.POINTER(ctypes.c_float),
+                                                     ctypes.POINTER(ctypes.c_longlong)]
     lib.kronmult_b200_needs_workspace.restype = c_int
     lib.kronmult_b200_needs_workspace.argtypes = [c_int, c_int, c_int]
     lib.kronmult_plan_execute.restype, lib.kronmult_plan_execute.argtypes = c_int, [c_vp, c_vp]
@@ -214,6 +241,95 @@ def kronmult_batched_host(matrix_count: int, matrix_size: int, matrix_list_batch
         _addr(output_batched), _addr(workspace_batched), int(nb_batch), int(device))
     if code != 0:
         raise KronmultError(code, "kronmult_batched_host")
+
+
+def build_asgard_batch(d: int, n: int, lda: int, cells: torch.Tensor, coeff: torch.Tensor, nterms: int, rows, cols,
+                       x: torch.Tensor, y: torch.Tensor, *, stream=None):
+    """Device-side pointer arrays of the ASGarD batch {(i, j, t)} (``kronmult_build_batch_*``).
+
+    ``cells`` int32 [num_elements, d] 1-D cell indices, ``coeff`` int64 [nterms*d] device addresses of the 1-D
+    coefficient matrices, ``rows`` / ``cols`` = (first, last+1) element ranges, ``x`` / ``y`` the stacked element
+    vectors.  Returns ``(A, in, out, nb)`` as int64 device tensors for ``kronmult_batched_const``."""
+    lib = load_library()
+    assert cells.dtype == torch.int32 and cells.is_contiguous() and coeff.dtype == torch.int64
+    nb = (rows[1] - rows[0]) * (cols[1] - cols[0]) * nterms
+    dev = x.device
+    A = torch.empty(max(1, nb * d), dtype=torch.int64, device=dev)
+    i_ = torch.empty(max(1, nb), dtype=torch.int64, device=dev)
+    o_ = torch.empty(max(1, nb), dtype=torch.int64, device=dev)
+    got = ctypes.c_longlong()
+    handle = 0 if stream is None else (stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream))
+    code = getattr(lib, f"kronmult_build_batch_{_suffix(x.dtype)}")(
+        int(d), int(n), int(lda), cells.data_ptr(), coeff.data_ptr(), int(nterms), int(rows[0]), int(rows[1]),
+        int(cols[0]), int(cols[1]), x.data_ptr(), y.data_ptr(), A.data_ptr(), i_.data_ptr(), o_.data_ptr(),
+        ctypes.byref(got), handle)
+    if code != 0:
+        raise KronmultError(code, "kronmult_build_batch")
+    assert got.value == nb
+    return A[: nb * d], i_[:nb], o_[:nb], nb
+
+
+class Comm:
+    """A ``kronmult_comm`` over the ranks of a ``torch.distributed`` job (one process per GPU): rank 0's
+    ncclUniqueId is broadcast with ``torch.distributed`` (plumbing), the communicator itself is the library's own."""
+
+    def __init__(self, dist=None, device=None):
+        import numpy as np
+        lib = load_library()
+        self.world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        self._h = ctypes.c_void_p()
+        ident = np.zeros(128, dtype=np.uint8)
+        if self.world > 1:
+            if self.rank == 0:
+                code = lib.kronmult_comm_unique_id(ident.ctypes.data)
+                if code != 0:
+                    raise KronmultError(code, "kronmult_comm_unique_id")
+            t = torch.from_numpy(ident)
+            if device is not None:
+                t = t.to(device)
+            dist.broadcast(t, 0)
+            ident = t.cpu().numpy().copy()
+        code = lib.kronmult_comm_create(ident.ctypes.data, self.world, self.rank, ctypes.byref(self._h))
+        if code != 0:
+            raise KronmultError(code, "kronmult_comm_create")
+
+    def last_collective(self) -> "tuple[float, int]":
+        ms, cnt = ctypes.c_float(), ctypes.c_longlong()
+        code = load_library().kronmult_comm_last_collective_ms(self._h, ctypes.byref(ms), ctypes.byref(cnt))
+        if code != 0:
+            raise KronmultError(code, "kronmult_comm_last_collective_ms")
+        return float(ms.value), int(cnt.value)
+
+    def destroy(self) -> None:
+        if self._h:
+            load_library().kronmult_comm_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def kronmult_batched_sharded(matrix_count: int, matrix_size: int, matrix_list_batched, matrix_stride: int,
+                             input_batched, output_batched, workspace_batched, nb_batch: int, shared_outputs,
+                             comm: "Comm", *, owner=None, dtype=torch.float64, stream=None) -> None:
+    """This rank's shard of a batch (``kronmult_batched_sharded_*``): ``shared_outputs`` lists the device
+    addresses of this rank's copies of the output vectors that were split across ranks (same order on every
+    rank); their partial sums are combined with one NCCL all-reduce inside the call."""
+    import numpy as np
+    lib = load_library()
+    sh = np.ascontiguousarray(np.asarray(shared_outputs, dtype=np.uint64))
+    ow = None if owner is None else np.ascontiguousarray(np.asarray(owner, dtype=np.int32))
+    handle = 0 if stream is None else (stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream))
+    code = getattr(lib, f"kronmult_batched_sharded_{_suffix(dtype)}")(
+        int(matrix_count), int(matrix_size), _addr(matrix_list_batched), int(matrix_stride), _addr(input_batched),
+        _addr(output_batched), _addr(workspace_batched), int(nb_batch), sh.ctypes.data if sh.size else 0, int(sh.size),
+        ow.ctypes.data if ow is not None else 0, comm._h, handle)
+    if code != 0:
+        raise KronmultError(code, "kronmult_batched_sharded")
 
 
 class Plan:

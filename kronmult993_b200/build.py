@@ -61,7 +61,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     for o, cmd, pr in procs:
         if pr.wait() != 0:
             raise subprocess.CalledProcessError(pr.returncode, cmd)
-    subprocess.run([_nvcc(), *ARCH, "-shared", "-o", LIB, *[o for o, _, _ in procs], "-lpthread"], check=True, cwd=CSRC)
+    subprocess.run([_nvcc(), *ARCH, "-shared", "-o", LIB, *[o for o, _, _ in procs], "-lpthread", "-ldl"], check=True, cwd=CSRC)
     return LIB
 
 

@@ -2,6 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace kron
 {
@@ -17,7 +20,8 @@ enum Path : int
     PATH_WSPEC   = 5, // n = 4, d = 5,6: warp-specialised two-phase kernel with 64-value register tiles
     PATH_WSPEC5  = 6, // n = 4, d = 5: two items per step, split rows, double-buffered exchange
     PATH_PAIRTILE = 7, // compile-time (n, d), n x n register tiles, two factors per shared-memory round trip
-    PATH_LAST    = PATH_PAIRTILE,
+    PATH_SYM5    = 8, // n = 4, d = 5: symmetric single-role kernel, one warp per item stream, in-place phases
+    PATH_LAST    = PATH_SYM5,
 };
 
 __host__ __device__ constexpr int ipow(int b, int e)
@@ -40,6 +44,61 @@ __device__ __forceinline__ void red_add(double *addr, double v)
 __device__ __forceinline__ void red_add(float *addr, float v)
 {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+
+// Per-device, per-kernel launch state: the opt-in to more than 48 KiB of dynamic shared memory
+// (cudaFuncAttributeMaxDynamicSharedMemorySize) and the occupancy of a kernel belong to a (function, device) pair,
+// not to the process -- a host thread that drives several GPUs (kronmult_batched_host_*(..., device)) needs both on
+// each of them.  `smem` is the largest dynamic shared-memory size the kernel is ever launched with on this device;
+// the attribute is only ever raised.  Thread-safe.
+struct KernelState
+{
+    int smem = -1; // opt-in already granted on this device (bytes), -1: never set
+    int occ  = 0;  // resident CTAs per SM for (threads, smem) of the last query
+    int occ_threads = 0, occ_smem = -1;
+};
+inline cudaError_t kernel_setup_any(const void *fn, int threads, int smem, int *ctas_per_sm)
+{
+    static std::mutex mtx;
+    static std::map<std::pair<const void *, int>, KernelState> states;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mtx);
+    KernelState &ks = states[std::make_pair(fn, dev)];
+    if (smem > ks.smem)
+    {
+        if (smem > 48 * 1024 || ks.smem > 48 * 1024)
+        {
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+        }
+        ks.smem = smem;
+    }
+    if (ctas_per_sm)
+    {
+        if (ks.occ_threads != threads || ks.occ_smem != smem)
+        {
+            int occ = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, (size_t)smem);
+            if (e != cudaSuccess) return e;
+            ks.occ = occ > 0 ? occ : 1;
+            ks.occ_threads = threads;
+            ks.occ_smem    = smem;
+        }
+        *ctas_per_sm = ks.occ;
+    }
+    return cudaSuccess;
+}
+template<typename K>
+inline cudaError_t kernel_setup(K kfn, int threads, int smem, int &ctas_per_sm)
+{
+    return kernel_setup_any(reinterpret_cast<const void *>(kfn), threads, smem, &ctas_per_sm);
+}
+template<typename K>
+inline cudaError_t kernel_setup(K kfn, int smem)
+{
+    return kernel_setup_any(reinterpret_cast<const void *>(kfn), 0, smem, nullptr);
 }
 
 __device__ __forceinline__ bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

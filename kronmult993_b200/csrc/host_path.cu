@@ -5,8 +5,9 @@
 // streamed through the GPU in chunks of items:
 //   host vectors/factors --(direct cudaMemcpyAsync when they are contiguous in host memory, else a
 //   multi-threaded gather into pinned staging)--> device chunk buffers --> the device path of this
-//   library (kronmult_batched_*_async) --> one device copy of every distinct output vector, which is
-//   seeded with the caller's current output values and copied back at the end.
+//   library (kronmult_batched_*_async) --> one device copy of every distinct output RANGE (overlapping or
+//   touching output vectors are merged into spans, so partial overlaps accumulate like the device path), which
+//   is seeded with the caller's current output values and copied back at the end.
 // Two chunk buffer sets on two streams overlap the copies of chunk c+1 with the kernel of chunk c.
 // Input and workspace arrays are never written (the contract would allow it, kronmult.hpp:72).
 #include "../../include/kronmult_b200.h"
@@ -23,14 +24,14 @@ namespace kron
 {
 
 template<typename T>
-__global__ void build_chunk_pointers(T *d_in, T *d_A, T *d_out, const int *__restrict__ slot, int count, int d,
-                                     int N, int nn, T **pin, const T **pA, T **pout)
+__global__ void build_chunk_pointers(T *d_in, T *d_A, T *d_out, const unsigned long long *__restrict__ out_off,
+                                     int count, int d, int N, int nn, T **pin, const T **pA, T **pout)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count)
     {
         pin[i]  = d_in + (size_t)i * N;
-        pout[i] = d_out + (size_t)slot[i] * N;
+        pout[i] = d_out + out_off[i]; // element offset of the item's output window in the device copy
     }
     if (i < count * d) pA[i] = d_A + (size_t)i * nn;
 }
@@ -61,6 +62,22 @@ struct Buffers
     }
 };
 
+// How the batch's output vectors map onto device memory.  Output vectors that overlap or touch in host memory
+// are merged into one SPAN (a maximal contiguous host range); every item's output is a window into its span's
+// device copy, so partially overlapping outputs accumulate correctly (the device path is atomic-class for any
+// aliasing, like kronmult.cu:126-129) and a contiguous output slab is one span = one copy each way.
+// Cached across calls: ASGarD passes the same pointer arrays every time step.
+struct OutputMap
+{
+    const void *out_array = nullptr; // identity of the caller's array ...
+    int nb = -1, N = 0, elem = 0;
+    unsigned long long hash = 0;     // ... and of its contents
+    std::vector<size_t> item_off;    // per item: element offset of its output in the device copy
+    struct Span { char *host; size_t elems, dev_off; };
+    std::vector<Span> spans;
+    size_t total_elems = 0;
+};
+
 struct HostContext
 {
     std::mutex mtx;
@@ -68,8 +85,82 @@ struct HostContext
     cudaStream_t stream[2] = {nullptr, nullptr};
     cudaEvent_t done[2]    = {nullptr, nullptr};
     int device             = -1;
+    OutputMap omap;
 };
-static HostContext g_ctx[16];
+constexpr int MAX_DEVICES = 64;
+static HostContext g_ctx[MAX_DEVICES];
+
+// restores the caller's current device on every exit path (the CPU flavour this mirrors has no such side effect)
+struct DeviceGuard
+{
+    int prev = -1;
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static unsigned long long hash_pointers(const void *const *p, size_t count)
+{
+    unsigned long long h = 0x9E3779B97F4A7C15ull;
+    for (size_t i = 0; i < count; ++i)
+    {
+        h ^= reinterpret_cast<unsigned long long>(p[i]) + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    }
+    return h;
+}
+
+template<typename T>
+static void build_output_map(OutputMap &om, T *const *out, int nb, int N)
+{
+    const unsigned long long h = hash_pointers(reinterpret_cast<const void *const *>(out), (size_t)nb);
+    if (om.out_array == out && om.nb == nb && om.N == N && om.elem == (int)sizeof(T) && om.hash == h) return; // cached
+    om.out_array = out; om.nb = nb; om.N = N; om.elem = (int)sizeof(T); om.hash = h;
+    // distinct output pointers (consecutive repeats are the common case)
+    std::vector<char *> uniq;
+    {
+        std::unordered_map<const void *, int> seen;
+        const T *prev = nullptr;
+        for (int k = 0; k < nb; ++k)
+        {
+            if (out[k] == prev) continue;
+            prev = out[k];
+            if (seen.emplace(out[k], 1).second) uniq.push_back(reinterpret_cast<char *>(out[k]));
+        }
+    }
+    std::sort(uniq.begin(), uniq.end());
+    // merge overlapping / touching ranges [p, p + N*s) into spans; an overlap that is not a whole number of
+    // elements apart cannot be expressed as element offsets -> kept as separate spans only if disjoint
+    const size_t bytes = (size_t)N * sizeof(T);
+    om.spans.clear();
+    std::unordered_map<const void *, size_t> dev_off; // element offset of every distinct output
+    size_t total = 0;
+    for (size_t u = 0; u < uniq.size(); ++u)
+    {
+        char *p = uniq[u];
+        if (!om.spans.empty())
+        {
+            OutputMap::Span &sp = om.spans.back();
+            char *end = sp.host + sp.elems * sizeof(T);
+            if (p <= end && (size_t)(p - sp.host) % sizeof(T) == 0)
+            {
+                const size_t off = (size_t)(p - sp.host) / sizeof(T);
+                if (off + N > sp.elems) { total += off + N - sp.elems; sp.elems = off + N; }
+                dev_off[p] = sp.dev_off + off;
+                continue;
+            }
+        }
+        om.spans.push_back({p, (size_t)N, total});
+        dev_off[p] = total;
+        total += N;
+        (void)bytes;
+    }
+    om.total_elems = total;
+    om.item_off.resize(nb);
+    const T *prev = nullptr; size_t prev_off = 0;
+    for (int k = 0; k < nb; ++k)
+    {
+        if (out[k] != prev) { prev = out[k]; prev_off = dev_off[out[k]]; }
+        om.item_off[k] = prev_off;
+    }
+}
 
 template<typename F>
 static void parallel_for(size_t count, size_t min_per_thread, F &&fn)
@@ -108,11 +199,21 @@ template<typename T>
 static int host_call(int d, int n, const T *const *A, int lda, T **in, T **out, int nb, int device)
 {
     if (nb <= 0) return 0;
-    if (d < 0 || n < 1 || lda < n || !A || !in || !out) return (int)cudaErrorInvalidValue;
-    if (device >= 0) KRON_TRY(cudaSetDevice(device));
+    if (d < 0 || n < 1 || lda < n || (!A && d > 0) || !in || !out) return (int)cudaErrorInvalidValue; // as dispatch()
+    DeviceGuard guard;
+    if (device >= 0)
+    {
+        int cur = -1;
+        KRON_TRY(cudaGetDevice(&cur));
+        if (cur != device)
+        {
+            KRON_TRY(cudaSetDevice(device));
+            guard.prev = cur;
+        }
+    }
     int dev = 0;
     KRON_TRY(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 16) return (int)cudaErrorInvalidDevice;
+    if (dev < 0 || dev >= MAX_DEVICES) return (int)cudaErrorInvalidDevice;
     long long N64 = 1;
     for (int i = 0; i < d; ++i)
     {
@@ -130,43 +231,25 @@ static int host_call(int d, int n, const T *const *A, int lda, T **in, T **out, 
         if (!cx.done[i]) KRON_TRY(cudaEventCreateWithFlags(&cx.done[i], cudaEventDisableTiming));
     }
 
-    // ---- distinct outputs -> slots (consecutive repeats are the common case)
-    std::vector<int> slot(nb);
-    std::vector<T *> uniq;
-    {
-        std::unordered_map<const void *, int> index;
-        T *prev = nullptr; int prev_slot = -1;
-        for (int k = 0; k < nb; ++k)
-        {
-            int sl;
-            if (prev_slot >= 0 && out[k] == prev) sl = prev_slot;
-            else
-            {
-                auto it = index.find(out[k]);
-                if (it == index.end())
-                {
-                    sl = (int)uniq.size();
-                    index.emplace(out[k], sl);
-                    uniq.push_back(out[k]);
-                }
-                else sl = it->second;
-            }
-            slot[k] = sl; prev = out[k]; prev_slot = sl;
-        }
-    }
-    const size_t U = uniq.size();
-    bool out_contig = true;
-    for (size_t u = 1; u < U && out_contig; ++u) out_contig = (uniq[u] == uniq[u - 1] + N);
-    KRON_TRY(cx.outbuf.ensure(U * N * s, out_contig ? 0 : U * N * s));
+    // ---- output vectors -> spans of the device copy (cached across calls with the same pointer array)
+    build_output_map<T>(cx.omap, out, nb, N);
+    const OutputMap &om = cx.omap;
+    const size_t U_el   = om.total_elems;
+    const bool few_spans = om.spans.size() <= 64;
+    KRON_TRY(cx.outbuf.ensure(U_el * s, few_spans ? 0 : U_el * s));
     T *d_out = static_cast<T *>(cx.outbuf.dev);
-    if (out_contig) KRON_TRY(cudaMemcpyAsync(d_out, uniq[0], U * N * s, cudaMemcpyHostToDevice, cx.stream[0]));
+    if (few_spans)
+    {
+        for (const auto &sp : om.spans)
+            KRON_TRY(cudaMemcpyAsync(d_out + sp.dev_off, sp.host, sp.elems * s, cudaMemcpyHostToDevice, cx.stream[0]));
+    }
     else
     {
         T *stage = static_cast<T *>(cx.outbuf.pinned);
-        parallel_for(U, 64, [&](size_t a, size_t b) {
-            for (size_t u = a; u < b; ++u) std::memcpy(stage + u * N, uniq[u], N * s);
+        parallel_for(om.spans.size(), 64, [&](size_t a, size_t b) {
+            for (size_t u = a; u < b; ++u) std::memcpy(stage + om.spans[u].dev_off, om.spans[u].host, om.spans[u].elems * s);
         });
-        KRON_TRY(cudaMemcpyAsync(d_out, stage, U * N * s, cudaMemcpyHostToDevice, cx.stream[0]));
+        KRON_TRY(cudaMemcpyAsync(d_out, stage, U_el * s, cudaMemcpyHostToDevice, cx.stream[0]));
     }
     KRON_TRY(cudaStreamSynchronize(cx.stream[0]));
 
@@ -175,8 +258,8 @@ static int host_call(int d, int n, const T *const *A, int lda, T **in, T **out, 
     C        = std::max<size_t>(1, std::min<size_t>(C, (size_t)nb));
     auto up  = [](size_t v) { return (v + 255) / 256 * 256; };
     const size_t o_in = 0, o_A = o_in + up(C * N * s), o_pin = o_A + up(C * d * nn * s), o_pA = o_pin + up(C * 8),
-                 o_pout = o_pA + up(C * d * 8), o_slot = o_pout + up(C * 8), dev_total = o_slot + up(C * 4);
-    const size_t h_in = 0, h_A = h_in + up(C * N * s), h_slot = h_A + up(C * d * nn * s), pin_total = h_slot + up(C * 4);
+                 o_pout = o_pA + up(C * d * 8), o_slot = o_pout + up(C * 8), dev_total = o_slot + up(C * 8);
+    const size_t h_in = 0, h_A = h_in + up(C * N * s), h_slot = h_A + up(C * d * nn * s), pin_total = h_slot + up(C * 8);
     for (int i = 0; i < 2; ++i) KRON_TRY(cx.set[i].ensure(dev_total, pin_total));
 
     int which = 0;
@@ -218,13 +301,14 @@ static int host_call(int d, int n, const T *const *A, int lda, T **in, T **out, 
                 KRON_TRY(cudaMemcpyAsync(dv + o_A, stage, nm * nn * s, cudaMemcpyHostToDevice, st));
             }
         }
-        std::memcpy(hp + h_slot, slot.data() + k0, cnt * 4);
-        KRON_TRY(cudaMemcpyAsync(dv + o_slot, hp + h_slot, cnt * 4, cudaMemcpyHostToDevice, st));
+        static_assert(sizeof(size_t) == 8, "output offsets travel as 64-bit values");
+        std::memcpy(hp + h_slot, om.item_off.data() + k0, cnt * 8);
+        KRON_TRY(cudaMemcpyAsync(dv + o_slot, hp + h_slot, cnt * 8, cudaMemcpyHostToDevice, st));
 
         const int total = (int)std::max(cnt, nm);
         build_chunk_pointers<T><<<(total + 255) / 256, 256, 0, st>>>(
             reinterpret_cast<T *>(dv + o_in), reinterpret_cast<T *>(dv + o_A), d_out,
-            reinterpret_cast<const int *>(dv + o_slot), (int)cnt, d, N, nn, reinterpret_cast<T **>(dv + o_pin),
+            reinterpret_cast<const unsigned long long *>(dv + o_slot), (int)cnt, d, N, nn, reinterpret_cast<T **>(dv + o_pin),
             reinterpret_cast<const T **>(dv + o_pA), reinterpret_cast<T **>(dv + o_pout));
         KRON_TRY(cudaGetLastError());
         int rc = async_call<T>(d, n, reinterpret_cast<const T *const *>(dv + o_pA), n,
@@ -236,13 +320,18 @@ static int host_call(int d, int n, const T *const *A, int lda, T **in, T **out, 
     KRON_TRY(cudaStreamSynchronize(cx.stream[1]));
 
     // ---- outputs back
-    if (out_contig) KRON_TRY(cudaMemcpy(uniq[0], d_out, U * N * s, cudaMemcpyDeviceToHost));
+    if (few_spans)
+    {
+        for (const auto &sp : om.spans)
+            KRON_TRY(cudaMemcpyAsync(sp.host, d_out + sp.dev_off, sp.elems * s, cudaMemcpyDeviceToHost, cx.stream[0]));
+        KRON_TRY(cudaStreamSynchronize(cx.stream[0]));
+    }
     else
     {
         T *stage = static_cast<T *>(cx.outbuf.pinned);
-        KRON_TRY(cudaMemcpy(stage, d_out, U * N * s, cudaMemcpyDeviceToHost));
-        parallel_for(U, 64, [&](size_t a, size_t b) {
-            for (size_t u = a; u < b; ++u) std::memcpy(uniq[u], stage + u * N, N * s);
+        KRON_TRY(cudaMemcpy(stage, d_out, U_el * s, cudaMemcpyDeviceToHost));
+        parallel_for(om.spans.size(), 64, [&](size_t a, size_t b) {
+            for (size_t u = a; u < b; ++u) std::memcpy(om.spans[u].host, stage + om.spans[u].dev_off, om.spans[u].elems * s);
         });
     }
     return 0;

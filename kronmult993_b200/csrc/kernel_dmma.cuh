@@ -239,13 +239,8 @@ static cudaError_t launch_dmma84(int sms, const double *const *A, int lda, doubl
                                  int nb, cudaStream_t st, std::atomic<long long> &launches)
 {
     using C = Dmma84;
-    static bool attr_done = false;
-    if (!attr_done)
-    {
-        cudaError_t e = cudaFuncSetAttribute(kron_dmma84_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    cudaError_t e = kernel_setup(kron_dmma84_kernel, C::SMEM); // per device (common.cuh)
+    if (e != cudaSuccess) return e;
     // one contiguous range of items per CTA (runs of equal output pointers stay together), one wave of CTAs
     long long grid = (long long)sms * 3;
     long long ipc  = ((long long)nb + grid - 1) / grid;
@@ -522,13 +517,8 @@ static cudaError_t launch_dmma8_tile4(int sms, int d, long long N, const double 
                                       int nb, cudaStream_t st, std::atomic<long long> &launches)
 {
     using C = Dmma84;
-    static bool attr_done = false;
-    if (!attr_done)
-    {
-        cudaError_t e = cudaFuncSetAttribute(kron_dmma8_tile4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE4_SMEM);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    cudaError_t e = kernel_setup(kron_dmma8_tile4_kernel, TILE4_SMEM);
+    if (e != cudaSuccess) return e;
     const int tpi            = (int)(N / C::N);
     const long long units    = (long long)nb * tpi;
     const long long max_grid = (long long)sms * 2;
@@ -543,13 +533,8 @@ static cudaError_t launch_dmma8_rows2(int sms, int d, long long N, const double 
                                       double *const *out, int nb, cudaStream_t st, std::atomic<long long> &launches)
 {
     using C = Dmma84;
-    static bool attr_done = false;
-    if (!attr_done)
-    {
-        cudaError_t e = cudaFuncSetAttribute(kron_dmma8_rows2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    cudaError_t e = kernel_setup(kron_dmma8_rows2_kernel, C::SMEM);
+    if (e != cudaSuccess) return e;
     const long long L = N / 64;
     const int tiles   = (int)(L / 64);
     long long chunk   = ((long long)nb * tiles) / ((long long)sms * 12);

@@ -279,9 +279,8 @@ static cudaError_t launch_pairpass(int sms, const T *const *A, T *const *src, T 
     else
     {
         auto kfn = kron_pairpass_kernel<T, n, GF, Q, FINAL>;
-        if (C::SMEM > 48 * 1024)
         {
-            cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+            cudaError_t e = kernel_setup(kfn, C::SMEM); // per device, cached (common.cuh)
             if (e != cudaSuccess) return e;
         }
         // contiguous unit ranges per CTA; at least ~8 units per CTA so that the pipeline has something to overlap

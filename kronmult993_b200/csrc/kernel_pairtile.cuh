@@ -847,9 +847,8 @@ static cudaError_t launch_pairtile(int sms, const T *const *A, int lda, T *const
     else
     {
         auto kfn = kron_pairtile_kernel<T, n, d>;
-        if (C::SMEM > 48 * 1024)
         {
-            cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+            cudaError_t e = kernel_setup(kfn, C::SMEM); // per device, cached (common.cuh)
             if (e != cudaSuccess) return e;
         }
         const long long want = (long long)sms * C::MINB;

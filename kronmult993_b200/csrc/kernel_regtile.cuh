@@ -458,13 +458,8 @@ static cudaError_t launch_regtile4(int sms, const T *const *A, int lda, T *const
 {
     using C  = Regtile4<T, D>;
     auto kfn = kron_regtile4_kernel<T, D, STAGE>;
-    static bool attr_done = false; // benign race: the attribute call is idempotent
-    if (!attr_done)
-    {
-        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    cudaError_t e = kernel_setup(kfn, C::SMEM); // per device (common.cuh)
+    if (e != cudaSuccess) return e;
     // consecutive items per stream: long runs of equal outputs merge in registers
     long long chunk = nb / ((long long)C::B * sms * C::MINB * 4);
     if (chunk < 1) chunk = 1;

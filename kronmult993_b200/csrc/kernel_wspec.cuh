@@ -442,16 +442,9 @@ static cudaError_t launch_wspec4(int sms, const T *const *A, int lda, T *const *
 {
     using C  = Wspec4<T, D>;
     auto kfn = kron_wspec4_kernel<T, D>;
-    static int ctas_per_sm = 0; // benign race: idempotent
-    if (ctas_per_sm == 0)
-    {
-        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-        if (e != cudaSuccess) return e;
-        int occ = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, C::THREADS, C::SMEM);
-        if (e != cudaSuccess) return e;
-        ctas_per_sm = occ > 0 ? occ : 1;
-    }
+    int ctas_per_sm = 0;
+    cudaError_t e = kernel_setup(kfn, C::THREADS, C::SMEM, ctas_per_sm); // per device (common.cuh)
+    if (e != cudaSuccess) return e;
     long long grid = (long long)sms * ctas_per_sm;
     long long ipc  = ((long long)nb + grid - 1) / grid; // items per CTA
     // CTA and stream boundaries on multiples of 32 items when there is enough work, so that ASGarD-style

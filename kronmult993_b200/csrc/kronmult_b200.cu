@@ -16,6 +16,7 @@
 #include "kernel_dmma.cuh"
 #include "kernel_wspec.cuh"
 #include "kernel_wspec5.cuh"
+#include "kernel_sym5.cuh"
 #include "kernel_pairtile.cuh"
 #include "kernel_pairpass.cuh"
 
@@ -196,9 +197,10 @@ template<typename T, int NT>
 static cudaError_t launch_pass(const PassParams<T> &p, int grid, int smem, cudaStream_t st)
 {
     auto kfn = kron_pass_kernel<T, NT>;
-    if (smem > 48 * 1024)
     {
-        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        // the opt-in is only ever raised (per device, common.cuh): two host threads with different shapes cannot
+        // lower each other's limit between the attribute call and the launch
+        cudaError_t e = kernel_setup(kfn, smem);
         if (e != cudaSuccess) return e;
     }
     kfn<<<grid, 256, smem, st>>>(p);
@@ -308,6 +310,11 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
         e = run_wspec5<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
         return e == cudaErrorNotSupported ? cudaErrorInvalidValue : e;
     }
+    if (force == PATH_SYM5)
+    {
+        e = run_sym5<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
+        return e == cudaErrorNotSupported ? cudaErrorInvalidValue : e;
+    }
     if (force == PATH_PAIRTILE)
     {
         e = run_pairtile<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches);
@@ -341,7 +348,7 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
             e = run_generic<T>(di, d, n, A, lda, in, out, nb, st, d - remaining, scratch, const_in);
         if (e != cudaErrorNotSupported) return e;
     }
-    e = run_wspec5<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
+    e = run_sym5<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
     if (e != cudaErrorNotSupported) return e;
     e = run_wspec<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
     if (e != cudaErrorNotSupported) return e;
@@ -542,6 +549,7 @@ int kronmult_b200_set_tuning(int knob, int value)
     if (knob == 2) { kron::g_wspec5_dbg.store(value); return 0; }
     if (knob == 3 && value >= 1 && value <= 220) { kron::g_generic_resident_kib.store(value); return 0; }
     if (knob == 4 && value >= 0 && value <= 227) { kron::g_pairtile_resident_kib.store(value); return 0; }
+    if (knob == 5) { kron::g_sym5_var.store(value); return 0; }
     return (int)cudaErrorInvalidValue;
 }
 int kronmult_b200_force_path(int path)

@@ -43,9 +43,11 @@ class Shard:
     split_keys: np.ndarray      # global out_off of the split output vectors (same on every rank)
 
 
-def shard_problem(full: HostProblem, rank: int, world: int, split_threshold: int = 0):
+def shard_problem(full: HostProblem, rank: int, world: int, split_threshold: int = 0, split_init: str = "zeros"):
     """Rank-local view of ``full``.  Local output slab = [owned outputs with their current values |
-    zero-initialised partial sums for the split outputs]."""
+    the split outputs].  ``split_init="zeros"``: zero-initialised partial sums (the caller reduces them itself);
+    ``"values"``: this rank's copy of every split vector with its current values, as
+    ``kronmult_batched_sharded_*`` expects (the library isolates, reduces and adds the partial sums)."""
     owner, red = partition_by_output(full.out_off, world, split_threshold)
     N, d = full.N, full.d
     mine = np.nonzero(owner == rank)[0]
@@ -57,7 +59,11 @@ def shard_problem(full: HostProblem, rank: int, world: int, split_threshold: int
     mo = full.mat_off.reshape(full.nb, d)[mine].ravel()
     mat_slab = full.mat_slab[(mo[:, None] + np.arange(span)[None, :]).ravel()]
     out_whole = full.out_slab[(whole_keys[:, None] + ar[None, :]).ravel()] if whole_keys.size else full.out_slab[:0]
-    out_slab = np.concatenate([out_whole, np.zeros(split_keys.size * N, dtype=full.out_slab.dtype)])
+    if split_init == "values" and split_keys.size:
+        out_split = full.out_slab[(split_keys[:, None] + ar[None, :]).ravel()]
+    else:
+        out_split = np.zeros(split_keys.size * N, dtype=full.out_slab.dtype)
+    out_slab = np.concatenate([out_whole, out_split])
     lut = {int(k): i * N for i, k in enumerate(whole_keys)}
     lut_s = {int(k): (whole_keys.size + i) * N for i, k in enumerate(split_keys)}
     out_off = np.array([lut_s[int(k)] if red[g] else lut[int(k)] for g, k in zip(mine, full.out_off[mine])],
@@ -66,6 +72,28 @@ def shard_problem(full: HostProblem, rank: int, world: int, split_threshold: int
                         np.arange(mine.size * d, dtype=np.int64) * span, in_slab,
                         np.arange(mine.size, dtype=np.int64) * N, out_slab, out_off)
     return Shard(local, mine, whole_keys, split_keys), owner, red
+
+
+def run_shard_on_device(full: HostProblem, rank: int, world: int, comm, device, split_threshold: int = 0, stream=None):
+    """One rank of the multi-GPU protocol on a real device: shard, ``kronmult_batched_sharded`` (the library's own
+    NCCL all-reduce for the split outputs, owner = rank j % world of the j-th split vector), returns
+    ``(shard, local_out_tensor, owner_of_split)``; the owner's copy of a split vector holds the final values."""
+    import torch
+
+    from . import batch
+
+    shard, owner, red = shard_problem(full, rank, world, split_threshold, split_init="values")
+    p = batch.from_host(shard.problem, device)
+    A, i_, o_, w_ = p.pointer_arrays()
+    N = full.N
+    nw = shard.whole_keys.size
+    s = p.out_slab.element_size()
+    shared = [p.out_slab.data_ptr() + (nw + j) * N * s for j in range(shard.split_keys.size)]
+    split_owner = np.arange(shard.split_keys.size, dtype=np.int32) % world
+    api.kronmult_batched_sharded(p.d, p.n, A, p.lda, i_, o_, w_, p.nb, shared, comm, owner=split_owner,
+                                 dtype=p.dtype, stream=stream)
+    torch.cuda.synchronize(device)
+    return shard, p.out_slab, split_owner
 
 
 def combine_shards(full: HostProblem, shard: Shard, local_out: np.ndarray, dist) -> np.ndarray:

@@ -85,7 +85,7 @@ def test_sweep_envelope_fp32(kron, oracle_mod, n, d):
 
 
 @pytest.mark.parametrize("path,n,d", [("tiny", 2, 2), ("tiny", 4, 2), ("tiny", 3, 2), ("tiny", 9, 1),
-                                      ("regtile", 4, 4), ("regtile", 4, 5), ("regtile", 4, 6), ("wspec", 4, 5), ("wspec", 4, 6), ("wspec5", 4, 5),
+                                      ("regtile", 4, 4), ("regtile", 4, 5), ("regtile", 4, 6), ("wspec", 4, 5), ("wspec", 4, 6), ("wspec5", 4, 5), ("sym5", 4, 5),
                                       ("generic", 4, 5), ("generic", 2, 2), ("generic", 8, 4)])
 @pytest.mark.parametrize("alias,kw", [("distinct", {}), ("runs", dict(items_per_output=32)),
                                       ("shuffled", dict(items_per_output=5)), ("ref", dict(nb_distinct=1))])
@@ -98,19 +98,21 @@ def test_every_kernel_family_every_aliasing(kron, oracle_mod, path, n, d, alias,
     assert kron.last_path().startswith(path)
 
 
+@pytest.mark.parametrize("path", ["sym5", "wspec5"])
 @pytest.mark.parametrize("dt", [torch.float64, torch.float32])
-@pytest.mark.parametrize("nb", [1, 2, 3, 5, 63, 64, 65, 129, 1000])
-def test_wspec5_ragged_batches(kron, oracle_mod, nb, dt):
-    """n = 4, d = 5: two item streams per CTA -- odd counts, a single item, runs that straddle streams."""
+@pytest.mark.parametrize("nb", [1, 2, 3, 5, 63, 64, 65, 129, 1000, 60000])
+def test_n4d5_ragged_batches(kron, oracle_mod, nb, dt, path):
+    """n = 4, d = 5: several item streams per CTA -- odd counts, a single item, runs that straddle streams."""
     for alias, kw in (("runs", dict(items_per_output=7)), ("distinct", {})):
         hp = batch.make_problem(5, 4, nb, dt, "cpu", seed=nb, alias=alias, lda=6, **kw).to_host()
-        _check(kron, oracle_mod, hp, "wspec5")
-        assert kron.last_path() == "wspec5"
+        _check(kron, oracle_mod, hp, path)
+        assert kron.last_path() == path
 
 
+@pytest.mark.parametrize("path", ["sym5", "wspec5"])
 @pytest.mark.parametrize("dt", [torch.float64, torch.float32])
 @pytest.mark.parametrize("layout", ["contiguous", "per_factor", "per_column", "asgard", "lda67", "misaligned"])
-def test_wspec5_factor_layouts(kron, oracle_mod, layout, dt):
+def test_n4d5_factor_layouts(kron, oracle_mod, layout, dt, path):
     """Every staging route of the five 4x4 factors: one TMA copy per item (dense, contiguous), one per factor
     (lda = 4, scattered), one per column (16-byte aligned columns), element-wise (anything else)."""
     kw = dict(alias="runs", items_per_output=6)
@@ -127,8 +129,8 @@ def test_wspec5_factor_layouts(kron, oracle_mod, layout, dt):
         hp = batch.make_problem(5, 4, 333, dt, "cpu", seed=9, matrices="reftest", **kw).to_host()
     else:
         hp = batch.make_problem(5, 4, 333, dt, "cpu", seed=10, misalign=1, **kw).to_host()
-    _check(kron, oracle_mod, hp, "wspec5")
-    assert kron.last_path() == "wspec5"
+    _check(kron, oracle_mod, hp, path)
+    assert kron.last_path() == path
 
 
 @pytest.mark.parametrize("n,d", [(2, 2), (4, 5), (4, 6), (5, 3), (8, 4)])

@@ -30,3 +30,32 @@ def test_reference_test_program_passes_against_this_library(kron):
     assert len(errs) == 2, res.stdout
     assert all(e <= 1e-7 for e in errs), errs  # the reference's own threshold
     assert all(e <= 1e-13 for e in errs), errs  # and what a correct implementation gives (tests/README.md:19-20)
+
+
+def _run_ref(kron, name, timeout):
+    path = os.path.join(ROOT, "oracle", "_ref", name)
+    if not os.path.exists(path):
+        pytest.skip(f"oracle/_ref/{name} not built (needs /root/reference at build time)")
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = os.path.dirname(kron.library_path()) + ":" + env.get("LD_LIBRARY_PATH", "")
+    return subprocess.run([path], capture_output=True, text=True, timeout=timeout, env=env)
+
+
+def test_reference_bench_program_runs_against_this_library(kron):
+    """tests/kronmult_bench_gpu.cpp:68-72: toy, small, medium, large, realistic (stride 67, 5 distinct outputs)."""
+    res = _run_ref(kron, "kronmult_bench_gpu", 600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    got = dict(re.findall(r"^(toy|small|medium|large|realistic): (\d+)ms", res.stdout, flags=re.M))
+    assert set(got) == {"toy", "small", "medium", "large", "realistic"}, res.stdout[-2000:]
+
+
+def test_reference_fullbench_program_runs_against_this_library(kron):
+    """tests/kronmult_fullbench_gpu.cpp:70-74: the whole sweep envelope n in [2,10] x d in [1,6] x level in [2,9]
+    (432 cases, one blocking call each, managed memory allocated per vector by the reference's harness)."""
+    if os.environ.get("KRON_RUN_FULLBENCH") != "1":
+        pytest.skip("opt-in (KRON_RUN_FULLBENCH=1): 11 minutes on a B200, nearly all of it the reference harness' "
+                    "per-vector cudaMallocManaged calls; log of a full run: profiles/reference_fullbench_gpu_against_b200_r02.txt")
+    res = _run_ref(kron, "kronmult_fullbench_gpu", 1500)
+    assert res.returncode == 0, res.stderr[-2000:]
+    rows = re.findall(r"^degree:(\d+) dimension:(\d+) level:(\d+) batch-size:(\d+): (\d+)ms", res.stdout, flags=re.M)
+    assert len(rows) == 9 * 6 * 8, len(rows)

@@ -43,6 +43,9 @@ def main():
     ap.add_argument("--plan", action="store_true", help="build an aliasing plan first and time its execution")
     ap.add_argument("--telemetry", action="store_true", help="NVML SM clock / power after every rep")
     ap.add_argument("--tune", default=None, help="knob=value[,knob=value] for kronmult_b200_set_tuning")
+    ap.add_argument("--ab", default=None,
+                    help="A/B list 'path[:knob=value[:knob=value]],...' timed on the SAME problem, interleaved --rounds times")
+    ap.add_argument("--rounds", type=int, default=1)
     ap.add_argument("--share-inputs", action="store_true",
                     help="ASGarD-style shared inputs through kronmult_batched_const: item t of output group i reads "
                          "input vector (i + t) mod #outputs, so every vector is read by r items of r consecutive groups")
@@ -81,6 +84,36 @@ def main():
             A, i, o, w = p.pointer_arrays()
         api.force_path(args.path)
         torch.cuda.synchronize()  # the problem was built on the default stream
+        if args.ab:
+            fl, by = p.flops(), p.algorithmic_bytes()
+            peak = (args.fp64_tflops if dt == torch.float64 else args.fp32_tflops) * 1e12
+            roof = max(by / (hbm * 1e9), fl / peak)
+            for rnd in range(args.rounds):
+                for ent in args.ab.split(","):
+                    parts = ent.split(":")
+                    api.force_path(parts[0])
+                    for kv in parts[1:]:
+                        kn, va = kv.split("=")
+                        api.set_tuning(int(kn), int(va))
+                    ts = []
+                    with torch.cuda.stream(stream):
+                        for rep in range(args.reps + 1):
+                            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                            e0.record(stream)
+                            api.kronmult_batched(p.d, p.n, A, p.lda, i, o, w, p.nb, dtype=dt, stream=stream)
+                            e1.record(stream)
+                            e1.synchronize()
+                            if rep >= 1:
+                                ts.append(e0.elapsed_time(e1))
+                    ts_s = sorted(ts)
+                    print(json.dumps({"config": name, "ab": ent, "round": rnd, "path": api.last_path(), "nb": nb,
+                                      "ms_min": round(ts_s[0], 4), "ms_med": round(ts_s[len(ts_s) // 2], 4),
+                                      "ms_last": round(ts[-1], 4), "frac_min": round(roof * 1e3 / ts_s[0], 4),
+                                      "frac_med": round(roof * 1e3 / ts_s[len(ts_s) // 2], 4)}), flush=True)
+            api.force_path("auto")
+            del p, A, i, o, w
+            torch.cuda.empty_cache()
+            continue
         times, tele = [], []
         plan, plan_info = None, {}
         if args.plan:
