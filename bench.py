@@ -18,6 +18,19 @@ e2e      same metric through the host-buffer C ABI (kronmult_batched_host_*): pi
          H2D of inputs/factors/outputs and D2H of the outputs inside the timed region.
 cpu_baseline  the reference's kronmult_omp (oracle/_ref, compiled from /root/reference where it lies;
          else the C port in oracle/) on the host cores, on a bounded sample of the same workload.
+configs  (N=1, or --all-configs) every other BASELINE.json configuration at full size -- C2, C3, C4a, C4b, C5-f32,
+         C1: sustained and best ms, GFLOP/s, algorithmic GB/s, fraction of the applicable roofline, kernel family,
+         and the relative L2 error of ONE application against the CPU oracle on a strided subset of output groups.
+blocking the real drop-in call kronmult_batched<double> (legacy stream, implicit plan scan, device sync) on the
+         headline workload: first (cold) call and plan-cached calls.
+asgard_layout  the headline shape with ASGarD-style factors: 4x4 windows into 5 shared 256x256 coefficient
+         matrices, lda = 256 (20 strided 32-byte column copies per item instead of one 640-byte copy).
+reference_gpu  the reference's kronmult_gpu/kronmult.cu rebuilt for sm_100a (oracle/_ref), same box, same run,
+         on 1/8 of the headline batch (it needs a real workspace per item and restores its clobbered inputs).
+ref5     the reference harness' own aliasing pattern -- 5 distinct outputs (tests/kronmult_bench_gpu.cpp:15) on
+         its `realistic` case (n=8, d=6, 3903 items of 262144 elements, stride 67) -- sharded over the N ranks
+         with every output group split: kronmult_batched_sharded_* with ONE ncclAllReduce (5 x 2 MiB) on the
+         timed path; reports the collective's device time and the parity of a small instance vs the oracle.
 """
 from __future__ import annotations
 
@@ -205,6 +218,224 @@ def run_reference_gpu_arm(args):
                       "alg_gbs": round(p.algorithmic_bytes() / per * 1e-9, 1)}), flush=True)
 
 
+def _tdt(dt):
+    import torch
+    return torch.float64 if dt == "f64" else torch.float32
+
+
+def _time_calls(fn, stream, warmup, steps):
+    """CUDA-event time of `steps` back-to-back calls (sustained) and of the best single call among them."""
+    import torch
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            fn()
+        stream.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ev[0].record(stream)
+        for i in range(steps):
+            fn()
+            ev[i + 1].record(stream)
+        stream.synchronize()
+    per = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+    return ev[0].elapsed_time(ev[steps]) / steps, min(per)
+
+
+def _roof_ms(p, dt, hbm):
+    return max(p.algorithmic_bytes() / (hbm * 1e9), p.flops() / (FP_PEAK_TFLOPS[dt] * 1e12)) * 1e3
+
+
+def _subset_parity(p, tdt, n_groups=48):
+    """relative L2 of ONE application vs the CPU oracle on a strided subset of output groups.
+    Must run before anything else touches p.out_slab; leaves the outputs one application further."""
+    import numpy as np
+    import torch
+    from kronmult993_b200 import api
+    from oracle import oracle
+    G = int(p.out_slab.numel() // p.N)
+    step = max(1, G // n_groups)
+    groups = torch.arange(0, G, step, dtype=torch.int64)[:n_groups]
+    hp, groups = p.select_outputs_to_host(groups)
+    A, i_, o_, w_ = p.pointer_arrays()
+    api.kronmult_batched(p.d, p.n, A, p.lda, i_, o_, w_, p.nb, dtype=tdt)
+    idx = (groups.to(p.device)[:, None] * p.N + torch.arange(p.N, device=p.device)[None, :]).flatten()
+    got = p.out_slab[idx].cpu().numpy()
+    exp = oracle.run(hp, "oracle", threads=os.cpu_count() or 1)
+    return float(oracle.rel_l2(got, exp)), int(hp.nb)
+
+
+def measure_config(name, hbm, steps, warmup, device, matrices="dense"):
+    import torch
+    from kronmult993_b200 import api, batch
+    d, n, nb, dt, r = CONFIGS[name]
+    tdt = _tdt(dt)
+    p = batch.make_problem(d, n, nb, tdt, device, seed=993, alias="runs" if r > 1 else "distinct", items_per_output=r,
+                           matrices=matrices)
+    torch.cuda.synchronize()
+    try:
+        err, n_checked = _subset_parity(p, tdt)
+    except Exception as ex:
+        err, n_checked = None, f"{type(ex).__name__}: {ex}"
+    A, i_, o_, w_ = p.pointer_arrays()
+    stream = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    time.sleep(1.0)  # every configuration starts from an idle GPU (the previous one leaves it power-capped)
+    ms, ms_min = _time_calls(lambda: api.kronmult_batched(p.d, p.n, A, p.lda, i_, o_, w_, p.nb, dtype=tdt, stream=stream),
+                             stream, warmup, steps)
+    roof = _roof_ms(p, dt, hbm)
+    bound = "hbm" if p.algorithmic_bytes() / (hbm * 1e9) >= p.flops() / (FP_PEAK_TFLOPS[dt] * 1e12) else "fp"
+    res = {"config": name, "workload": workload_name(name, d, n, nb, dt, r) + (f", {matrices} factors lda={p.lda}" if matrices != "dense" else ""),
+           "path": api.last_path(), "ms": round(ms, 4), "ms_min": round(ms_min, 4),
+           "gflops": round(p.flops() / ms * 1e-6, 1), "alg_gbs": round(p.algorithmic_bytes() / ms * 1e-6, 1),
+           "bound": bound, "roofline_ms": round(roof, 4), "frac": round(roof / ms, 4), "frac_best": round(roof / ms_min, 4),
+           "rel_l2_vs_oracle": err, "parity_items": n_checked, "tol": 1e-12 if dt == "f64" else 1e-5}
+    del p, A, i_, o_, w_
+    torch.cuda.empty_cache()
+    return res
+
+
+def measure_blocking(p, tdt, A, i_, o_, w_, reps=5):
+    """The reference-facing drop-in call itself: kronmult_batched<T> = legacy default stream + the implicit plan
+    scan (1 kernel + a 32-byte D2H) + cudaDeviceSynchronize (kronmult.cu:191-196).  Wall clock around the call."""
+    import torch
+    from kronmult993_b200 import api
+    torch.cuda.synchronize()
+    h0, b0 = api.plan_cache_counters()
+    ts = []
+    for _ in range(reps + 1):
+        t0 = time.perf_counter()
+        api.kronmult_batched(p.d, p.n, A, p.lda, i_, o_, w_, p.nb, dtype=tdt)  # stream=None: the blocking entry
+        ts.append((time.perf_counter() - t0) * 1e3)
+    h1, b1 = api.plan_cache_counters()
+    return {"cold_ms": round(ts[0], 3), "plan_cached_ms": round(sum(ts[1:]) / reps, 3), "plan_cached_ms_min": round(min(ts[1:]), 3),
+            "plan_cache_hits": h1 - h0, "plans_built": b1 - b0,
+            "note": "kronmult_batched_f64/_f32 (what kronmult_batched<T> of include/kronmult.cuh forwards to): "
+                    "host wall clock incl. the per-call run-count scan and cudaDeviceSynchronize"}
+
+
+def measure_reference_gpu(name, steps, device):
+    """The reference CUDA kernel rebuilt for sm_100a on 1/8 of the batch (it needs nb real workspaces)."""
+    import torch
+    from kronmult993_b200 import batch
+    lib_path = os.path.join(ROOT, "oracle", "_ref", "libkronmult_refgpu.so")
+    if not os.path.exists(lib_path):
+        return {"unavailable": "oracle/_ref/libkronmult_refgpu.so not built"}
+    d, n, nb, dt, r = CONFIGS[name]
+    nb //= 8
+    lib = ctypes.CDLL(lib_path, mode=ctypes.RTLD_LOCAL)
+    tdt = _tdt(dt)
+    p = batch.make_problem(d, n, nb, tdt, device, seed=993, alias="runs" if r > 1 else "distinct", items_per_output=r)
+    p.alloc_workspaces()
+    A, i_, o_, w_ = p.pointer_arrays()
+    fn = getattr(lib, f"refgpu_kronmult_batched_{dt}")
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                   ctypes.c_void_p, ctypes.c_int]
+    backup = p.in_slab.clone()
+    times = []
+    for s_ in range(1 + steps):
+        p.in_slab.copy_(backup)  # the reference clobbers its input (kronmult.cu:115-121)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(d, n, A.data_ptr(), p.lda, i_.data_ptr(), o_.data_ptr(), w_.data_ptr(), nb)
+        e1.record(); e1.synchronize()
+        if rc != 0:
+            return {"unavailable": f"reference kernel returned CUDA error {rc}"}
+        if s_ >= 1:
+            times.append(e0.elapsed_time(e1))
+    ms = sum(times) / len(times)
+    res = {"impl": "kronmult_gpu/kronmult.cu of the reference, built -arch=sm_100a (oracle/_ref/libkronmult_refgpu.so)",
+           "workload": workload_name(name, d, n, nb, dt, r) + " (1/8 of the batch)", "ms": round(ms, 3),
+           "gflops": round(p.flops() / ms * 1e-6, 1), "alg_gbs": round(p.algorithmic_bytes() / ms * 1e-6, 1), "steps": steps}
+    del p, backup, A, i_, o_, w_
+    torch.cuda.empty_cache()
+    return res
+
+
+def measure_ref5(world, rank, local, dist, steps, warmup):
+    """The reference harness' 5-distinct-outputs pattern on its `realistic` case, every output group split over the
+    ranks: kronmult_batched_sharded_* = shard kernel(s) + ONE ncclAllReduce + the owners' add, all on one stream."""
+    import numpy as np
+    import torch
+    from kronmult993_b200 import api, batch, partition
+    dev = torch.device("cuda", local)
+    comm = api.Comm(dist if world > 1 else None, device=dev)
+    out = {}
+    # ---- parity on the reference's `medium` case (n=6, d=3, 384 items, 5 outputs) against the oracle
+    try:
+        from oracle import oracle
+        full = batch.reference_case("medium", torch.float64, "cpu", seed=77).to_host()
+        shard, local_out, split_owner = partition.run_shard_on_device(full, rank, world, comm, dev, split_threshold=1)
+        N = full.N
+        nw = shard.whole_keys.size
+        merged = torch.zeros(full.out_slab.size, dtype=torch.float64, device=dev)
+        for j, key in enumerate(shard.split_keys):
+            if split_owner[j] == rank:
+                merged[int(key): int(key) + N] = local_out[(nw + j) * N: (nw + j + 1) * N]
+        for j, key in enumerate(shard.whole_keys):
+            merged[int(key): int(key) + N] = local_out[j * N: (j + 1) * N]
+        if world > 1:
+            dist.all_reduce(merged)
+        if rank == 0:
+            exp = oracle.run(full, "oracle", threads=1)
+            out["rel_l2_vs_oracle"] = float(oracle.rel_l2(merged.cpu().numpy(), exp))
+            out["parity_case"] = f"reference `medium` (n=6 d=3 nb={full.nb}, stride 67, 5 outputs), {int(shard.split_keys.size)} split groups"
+    except Exception as ex:
+        out["rel_l2_vs_oracle"] = None
+        out["parity_error"] = f"{type(ex).__name__}: {ex}"
+    # ---- timing on `realistic`: this rank's slice of every output group
+    n, d, level = batch.REFERENCE_CASES["realistic"]
+    nb_total = batch.compute_batch_size(n, d, level, 5)
+    g_full, n_out = batch.output_groups(nb_total, "ref", nb_distinct=5)
+    owner, red = partition.partition_by_output(g_full.numpy(), world, split_threshold=1)
+    mine = np.nonzero(owner == rank)[0]
+    p = batch.make_problem(d, n, int(mine.size), torch.float64, dev, seed=993 + rank, alias="ref", nb_distinct=5,
+                           matrices="reftest")
+    N = p.N
+    p.out_off = torch.from_numpy(g_full.numpy()[mine] * N).to(dev)  # the groups of MY items
+    p.out_slab = torch.randn(n_out * N, dtype=torch.float64, device=dev)
+    A, i_, o_, w_ = p.pointer_arrays()
+    shared = [p.out_slab.data_ptr() + j * N * 8 for j in range(n_out)] if world > 1 and int(red.sum()) > 0 else []
+    stream = torch.cuda.Stream()
+    torch.cuda.synchronize()
+
+    def call():
+        api.kronmult_batched_sharded(d, n, A, p.lda, i_, o_, w_, p.nb, shared, comm, owner=None, dtype=torch.float64,
+                                     stream=stream)
+    coll = []
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            call()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            call()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms_c, ncoll = comm.last_collective()
+    t = torch.tensor([e0.elapsed_time(e1) / steps, ms_c], dtype=torch.float64, device=dev)
+    fl = torch.tensor([float(p.flops())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(fl)
+    ms = float(t[0].item())
+    out.update({"workload": f"reference `realistic`: f64 d={d} n={n} (N={N}) nb={nb_total} items, stride 67, 5 distinct outputs "
+                            f"(tests/kronmult_bench_gpu.cpp:15,72), every group split over {world} rank(s)",
+                "ms_per_step": round(ms, 4), "gflops": round(float(fl.item()) / ms * 1e-6, 1),
+                "collective": (f"ncclAllReduce of {n_out} x {N * 8 >> 10} KiB partial vectors, in place, on the timed stream"
+                               if shared else "none (one rank owns every output)"),
+                "collective_ms_last": round(float(t[1].item()), 4), "collectives_issued": int(ncoll),
+                "path": api.last_path(), "steps": steps})
+    comm.destroy()
+    del p, A, i_, o_, w_
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -217,6 +448,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--all-configs", action="store_true", help="measure the `configs` block at N > 1 too (rank 0 only)")
+    ap.add_argument("--no-extras", action="store_true", help="headline only: skip configs / blocking / asgard / reference_gpu / ref5")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -224,6 +457,12 @@ def main():
         return run_reference_arm(args)
     if args.impl == "reference_gpu":
         return run_reference_gpu_arm(args)
+
+    # stdout carries exactly ONE line (the JSON record): NCCL prints its version banner to the C-level stdout at the
+    # first communicator creation, so everything else in this process goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import numpy as np
     import torch
@@ -297,10 +536,52 @@ def main():
     sec_step = ms_total * 1e-3 / args.steps
     value = flops_total / sec_step * 1e-9
 
+    traffic = ncu_traffic(args.config, p)
     # ---- end-to-end through the host-buffer C ABI (pinned host memory, copies inside the timed region)
     e2e = None
     if not args.no_e2e:
         e2e = measure_e2e(args, p, tdt, dt, world, rank, local, dist)
+
+    # ---- the multi-GPU fallback collective on the reference harness' own aliasing pattern (every rank takes part)
+    extras = {}
+    if not args.no_extras:
+        try:
+            extras["ref5"] = measure_ref5(world, rank, local, dist, steps=10, warmup=3)
+        except Exception as ex:
+            extras["ref5"] = {"error": f"{type(ex).__name__}: {ex}"}
+    # ---- rank 0 only: the drop-in blocking call, the ASGarD factor layout, the other BASELINE configurations and
+    # the reference CUDA kernel -- after the headline so that they cannot disturb it
+    if rank == 0 and not args.no_extras:
+        hbm_x, _ = measured_hbm_gbs()
+        try:
+            extras["blocking"] = measure_blocking(p, tdt, A, i_, o_, w_)
+        except Exception as ex:
+            extras["blocking"] = {"error": f"{type(ex).__name__}: {ex}"}
+    if not args.no_extras:
+        del p, A, i_, o_, w_
+        torch.cuda.empty_cache()
+    if rank == 0 and not args.no_extras and args.scale == 1.0:
+        dev_s = f"cuda:{local}"
+        try:
+            extras["asgard_layout"] = measure_config(args.config, hbm_x, 10, 3, dev_s, matrices="asgard")
+        except Exception as ex:
+            extras["asgard_layout"] = {"error": f"{type(ex).__name__}: {ex}"}
+        if world == 1 or args.all_configs:
+            cfgs = []
+            for name in ("c2", "c3", "c4a", "c4b", "c5_f32", "c5_f64", "c1"):
+                if name == args.config:
+                    continue
+                try:
+                    cfgs.append(measure_config(name, hbm_x, 10, 3, dev_s))
+                except Exception as ex:
+                    cfgs.append({"config": name, "error": f"{type(ex).__name__}: {ex}"})
+            extras["configs"] = cfgs
+            try:
+                extras["reference_gpu"] = measure_reference_gpu(args.config, 2, dev_s)
+            except Exception as ex:
+                extras["reference_gpu"] = {"error": f"{type(ex).__name__}: {ex}"}
+    if world > 1:
+        dist.barrier()
 
     if rank == 0:
         hbm, hbm_src = measured_hbm_gbs()
@@ -309,7 +590,9 @@ def main():
         fp_peak = FP_PEAK_TFLOPS[dt]
         roofline = {
             "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s",
-            "frac": round(achieved / hbm, 4), "traffic": ncu_traffic(args.config, p),
+            "frac": round(achieved / hbm, 4), "traffic": traffic,
+            "traffic_source": "static: dram__bytes_read+write per item of the committed ncu --set full capture of this "
+                              "kernel (profiles/ncu_traffic.json) x items per launch -- not measured in this run",
             "peak_source": f"{hbm_src} (MEASURED_PEAKS.json copy bandwidth)",
             "kernel": path, "launch_ms": round(launch_s * 1e3, 4),
             "alg_bytes_per_launch": bytes_rank,
@@ -340,7 +623,12 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches_total),
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        ref_gpu = extras.get("reference_gpu")
+        if isinstance(ref_gpu, dict) and ref_gpu.get("gflops"):
+            ref_gpu["speedup_of_this_library"] = round(value / world / ref_gpu["gflops"], 1)
+        line.update(extras)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
@@ -396,7 +684,7 @@ def measure_e2e(args, p, tdt, dt, world, rank, local, dist):
         dt_s = time.perf_counter() - t0
         t = torch.tensor([dt_s], dtype=torch.float64, device=f"cuda:{local}")
         fl = torch.tensor([float(items * 2 * d * n ** (d + 1))], dtype=torch.float64, device=f"cuda:{local}")
-        by = torch.tensor([float(items * per_item + items * 4 + n_out * N * s_el), float(n_out * N * s_el)],
+        by = torch.tensor([float(items * per_item + items * 8 + n_out * N * s_el), float(n_out * N * s_el)],
                           dtype=torch.float64, device=f"cuda:{local}")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(fl); dist.all_reduce(by)
@@ -404,6 +692,7 @@ def measure_e2e(args, p, tdt, dt, world, rank, local, dist):
         return {"value": round(float(fl.item()) / sec * 1e-9, 2), "unit": "GFLOP/s",
                 "h2d_bytes_per_step": int(by[0].item()), "d2h_bytes_per_step": int(by[1].item()),
                 "ms_per_step": round(sec * 1e3, 2), "steps": args.e2e_steps,
+                "h2d_gbs_per_gpu": round(float(by[0].item()) / world / sec * 1e-9, 2),
                 "items": int(items * world) if items == p.nb else int(items),
                 "note": ("whole per-rank batch" if items == p.nb else f"{items} of {p.nb} items per rank fit host RAM")
                         + "; host pointer arrays -> pinned staging -> H2D -> kernel -> D2H, wall clock, max over ranks"}
