@@ -165,7 +165,12 @@ int kronmult_b200_force_path(int path);
  *            (default 56); longer vectors take the tiled multi-pass route, which works in place in `in`.
  *         4: largest vector, in KiB, that the pairtile family keeps resident (default 227 = whatever fits); smaller
  *            values send long vectors through the pairtile multi-pass route (development: resident measured faster).
- *         5: variant of the n=4, d=5 kernel (development; only in builds with -DKRON_SYM5_VARIANTS). */
+ *         5: variant of the n=4, d=5 kernel (development; only in builds with -DKRON_SYM5_VARIANTS).
+ *         6: multi-pass routes (vectors beyond shared memory): MiB of vectors per chunk of items whose passes run back
+ *            to back so that the intermediate stays in L2 (0 = pass by pass over the whole batch; -1 = automatic,
+ *            the default: 32 MiB for routes of three or more passes, where it measured 29 % faster, else 0).
+ *         7: 1 = drop the dead intermediate from L2 with discard.global.L2 after a chunk's last pass (default 0).
+ *         8: internal streams the chunks of knob 6 are spread over (default 3; 1 = the caller's stream only). */
 int kronmult_b200_set_tuning(int knob, int value);
 
 #ifdef __cplusplus

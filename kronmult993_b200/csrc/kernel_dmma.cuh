@@ -569,9 +569,27 @@ static cudaError_t run_dmma(int sms, int d, int n, const T *const *A, int lda, T
             last_path = "dmma-multipass";
             // scratch != nullptr: `in` is read-only, pass A writes into the scratch vectors and the rest works there
             T *const *work = scratch ? scratch : in;
-            cudaError_t e  = launch_dmma8_tile4(sms, d, N, A, lda, in, work, nb, st, launches);
+            if (d == 6)
+            {
+                // both passes chunk by chunk, so that pass B reads pass A's result from L2 (common.cuh)
+                const long long cb = multipass_chunk_items(nb, N * 8, 2, 8);
+                ChunkStreams cs;
+                cudaError_t e = cs.begin(st, (nb + cb - 1) / cb);
+                if (e != cudaSuccess) return e;
+                for (long long k0 = 0; k0 < nb; k0 += cb)
+                {
+                    const int cnt     = (int)(nb - k0 < cb ? nb - k0 : cb);
+                    cudaStream_t sc   = cs.pick();
+                    e = launch_dmma8_tile4(sms, d, N, A + k0 * d, lda, in + k0, work + k0, cnt, sc, launches);
+                    if (e == cudaSuccess) e = launch_dmma8_rows2(sms, d, N, A + k0 * d, lda, work + k0, out + k0, cnt, sc, launches);
+                    if (e == cudaSuccess) e = launch_discard<T>(work + k0, cnt, N, sc);
+                    if (e != cudaSuccess) break;
+                }
+                const cudaError_t j = cs.end();
+                return e != cudaSuccess ? e : j;
+            }
+            cudaError_t e = launch_dmma8_tile4(sms, d, N, A, lda, in, work, nb, st, launches);
             if (e != cudaSuccess) return e;
-            if (d == 6) return launch_dmma8_rows2(sms, d, N, A, lda, work, out, nb, st, launches);
             *remaining = 1;
             return cudaSuccess;
         }

@@ -309,6 +309,10 @@ cudaError_t run_pairpass(int sms, int d, int n, const T *const *A, int lda, T *c
                          cudaStream_t st, std::atomic<long long> &launches, T *const *scratch);
 
 template<typename T, int n>
+static cudaError_t run_pairpass_chunk(int sms, int d, const T *const *A, int lda, T *const *in, T *const *out, int nb,
+                                      cudaStream_t st, std::atomic<long long> &launches, T *const *scratch, long long N);
+
+template<typename T, int n>
 static cudaError_t run_pairpass_n(int sms, int d, const T *const *A, int lda, T *const *in, T *const *out, int nb,
                                   cudaStream_t st, std::atomic<long long> &launches, T *const *scratch)
 {
@@ -316,11 +320,37 @@ static cudaError_t run_pairpass_n(int sms, int d, const T *const *A, int lda, T 
     static_assert(GM >= 3, "tiles of at least three indices");
     if (d <= GM) return cudaErrorNotSupported;
     if (GM > 3 && d - GM > 2) return cudaErrorNotSupported; // non-final later passes are only built for GM = 3
+    long long N = 1;
+    for (int i = 0; i < d; ++i) N *= n;
+    // chunks of items whose vectors stay in L2 between the passes (common.cuh); all passes of a chunk, then the next
+    const int passes   = 1 + (d - GM + 1) / 2;
+    const long long cb = multipass_chunk_items(nb, N * (long long)sizeof(T), passes);
+    if (cb < nb)
+    {
+        ChunkStreams cs;
+        cudaError_t e = cs.begin(st, (nb + cb - 1) / cb);
+        if (e != cudaSuccess) return e;
+        for (long long k0 = 0; k0 < nb; k0 += cb)
+        {
+            const int cnt = (int)(nb - k0 < cb ? nb - k0 : cb);
+            e = run_pairpass_chunk<T, n>(sms, d, A + k0 * d, lda, in + k0, out + k0, cnt, cs.pick(), launches,
+                                         scratch ? scratch + k0 : nullptr, N);
+            if (e != cudaSuccess) break;
+        }
+        const cudaError_t j = cs.end();
+        return e != cudaSuccess ? e : j;
+    }
+    return run_pairpass_chunk<T, n>(sms, d, A, lda, in, out, nb, st, launches, scratch, N);
+}
+
+template<typename T, int n>
+static cudaError_t run_pairpass_chunk(int sms, int d, const T *const *A, int lda, T *const *in, T *const *out, int nb,
+                                      cudaStream_t st, std::atomic<long long> &launches, T *const *scratch, long long N)
+{
+    constexpr int GM = pairpass_gmax<T>(n);
     T *const *work = scratch ? scratch : in;
     PassArgs pa{};
     pa.lda = lda; pa.nb = nb; pa.d = d;
-    long long N = 1;
-    for (int i = 0; i < d; ++i) N *= n;
 
     // pass 1: the GM fastest factors on contiguous tiles
     pa.j0 = d - GM; pa.L = 1; pa.lblocks = 1;
@@ -352,7 +382,8 @@ static cudaError_t run_pairpass_n(int sms, int d, const T *const *A, int lda, T 
         if (e != cudaSuccess) return e;
         done += g;
     }
-    return cudaSuccess;
+    // the intermediate vectors are dead: drop their (dirty) lines from L2 instead of writing them back
+    return launch_discard<T>(work, nb, N, st);
 }
 
 } // namespace kron

@@ -550,6 +550,9 @@ int kronmult_b200_set_tuning(int knob, int value)
     if (knob == 3 && value >= 1 && value <= 220) { kron::g_generic_resident_kib.store(value); return 0; }
     if (knob == 4 && value >= 0 && value <= 227) { kron::g_pairtile_resident_kib.store(value); return 0; }
     if (knob == 5) { kron::g_sym5_var.store(value); return 0; }
+    if (knob == 6 && value >= -1 && value <= 4096) { kron::multipass_chunk_mib().store(value); return 0; }
+    if (knob == 7) { kron::multipass_discard().store(value ? 1 : 0); return 0; }
+    if (knob == 8 && value >= 1 && value <= 4) { kron::multipass_streams().store(value); return 0; }
     return (int)cudaErrorInvalidValue;
 }
 int kronmult_b200_force_path(int path)

@@ -76,8 +76,10 @@ def test_sweep_envelope_fp64(kron, oracle_mod, n, d):
     _check(kron, oracle_mod, hp)
 
 
-@pytest.mark.parametrize("n,d", [(2, 2), (2, 5), (3, 4), (4, 3), (4, 4), (4, 5), (4, 6), (6, 3), (8, 2), (8, 4), (10, 3)])
+@pytest.mark.parametrize("n,d", SWEEP)
 def test_sweep_envelope_fp32(kron, oracle_mod, n, d):
+    """Every shape of the envelope through the AUTOMATIC dispatcher in single precision too (the fp32-only tiny
+    shapes (7,2) (9,2) (10,2) (5,3) (3,4) included)."""
     nb = max(3, min(300, 200000 // n ** d))
     hp = batch.make_problem(d, n, nb, torch.float32, "cpu", seed=n * 10 + d, alias="runs", items_per_output=3,
                             lda=n + 3).to_host()
