@@ -170,7 +170,9 @@ int kronmult_b200_force_path(int path);
  *            to back so that the intermediate stays in L2 (0 = pass by pass over the whole batch; -1 = automatic,
  *            the default: 32 MiB for routes of three or more passes, where it measured 29 % faster, else 0).
  *         7: 1 = drop the dead intermediate from L2 with discard.global.L2 after a chunk's last pass (default 0).
- *         8: internal streams the chunks of knob 6 are spread over (default 3; 1 = the caller's stream only). */
+ *         8: internal streams the chunks of knob 6 are spread over (default 3; 1 = the caller's stream only).
+ *         9: 1 (default) = the one-thread-per-item kernels stage items of 128..512 bytes through shared memory with
+ *            coalesced cp.async copies; 0 = every thread loads its own item (round-1 kernel). */
 int kronmult_b200_set_tuning(int knob, int value);
 
 #ifdef __cplusplus

@@ -238,9 +238,27 @@ static cudaError_t run_generic(const DeviceInfo &di, int d, int n, const T *cons
 // ----------------------------------------------------------------------------------------------
 // tiny path
 // ----------------------------------------------------------------------------------------------
+static std::atomic<int> g_tiny_staged{1}; // knob 9: 1 = items of 128 bytes and more are staged through shared memory
+
 template<typename T, int n, int d>
 static cudaError_t launch_tiny(const T *const *A, int lda, T *const *in, T *const *out, int nb, cudaStream_t st)
 {
+    using CS = TinyStaged<T, n, d>;
+    if constexpr (CS::OK)
+    {
+        if (g_tiny_staged.load(std::memory_order_relaxed))
+        {
+            auto kfn = kron_tiny_staged_kernel<T, n, d>;
+            cudaError_t e = kernel_setup(kfn, CS::SMEM);
+            if (e != cudaSuccess) return e;
+            const int per  = CS::WARPS * 32;
+            const int grid = (nb + per - 1) / per;
+            kfn<<<grid, per, CS::SMEM, st>>>(A, in, out, lda, nb);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            t_last_path = "tiny";
+            return cudaGetLastError();
+        }
+    }
     const int threads = 128;
     const int grid    = (nb + threads - 1) / threads;
     kron_tiny_kernel<T, n, d><<<grid, threads, 0, st>>>(A, in, out, lda, nb);
@@ -553,6 +571,7 @@ int kronmult_b200_set_tuning(int knob, int value)
     if (knob == 6 && value >= -1 && value <= 4096) { kron::multipass_chunk_mib().store(value); return 0; }
     if (knob == 7) { kron::multipass_discard().store(value ? 1 : 0); return 0; }
     if (knob == 8 && value >= 1 && value <= 4) { kron::multipass_streams().store(value); return 0; }
+    if (knob == 9) { kron::g_tiny_staged.store(value ? 1 : 0); return 0; }
     return (int)cudaErrorInvalidValue;
 }
 int kronmult_b200_force_path(int path)
