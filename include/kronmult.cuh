@@ -30,6 +30,9 @@ __host__ int pow_int(int const number, int const power);
 //    untouched whenever N fits on-chip; workspace is never needed);
 //  * sizes are not validated; the call blocks until the result is visible and returns the CUDA
 //    status (cudaSuccess, or the launch/synchronisation error).
+// Limits of this implementation (the reference accepts any size and then overflows its int size_input silently,
+// kronmult.cu:180): matrix_size <= 32 and matrix_size^matrix_count < 2^31, else cudaErrorInvalidValue.  The
+// reference's own envelope is matrix_size <= 10, matrix_count <= 6 (tests/kronmult_fullbench_gpu.cpp:70-74).
 template<typename T>
 __host__ cudaError kronmult_batched(int const matrix_count, int const matrix_size,
                                     T const *const matrix_list_batched[], int const matrix_stride,

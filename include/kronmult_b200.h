@@ -17,6 +17,7 @@
  *   ws   workspace_batched     DEVICE array of nb DEVICE pointers (may be clobbered; may be NULL here:
  *                              this implementation never dereferences it)
  *   nb   nb_batch              number of batch items (0 is a no-op)
+ * Limits: n <= 32 and n^d < 2^31 (cudaErrorInvalidValue otherwise; the reference's envelope is n <= 10, d <= 6).
  */
 #ifndef KRONMULT_B200_H
 #define KRONMULT_B200_H

@@ -535,6 +535,10 @@ __device__ __forceinline__ void pair_tile_split(typename C::T *__restrict__ vec,
             for (int j = 0; j < CB; ++j) Z[a][j] = x[a * G::sA_ph + (b0 + j) * G::sB_ph];
     }
 
+    // The two lanes that share this tile both read ALL of it above and store their own columns in place below:
+    // order the partner's loads before my stores.  Partners (adjacent lanes, same tile, same flag, same trip count)
+    // follow identical control flow, so they are in the same convergence group.
+    if constexpr (!REGFLUSH) __syncwarp(__activemask());
     const T *__restrict__ Ma = mats + G::ja * n * C::RP;
 #pragma unroll
     for (int h = 0; h < C::HB; ++h)
