@@ -44,9 +44,24 @@ def _sources():
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Build (if stale) under an exclusive file lock: torchrun starts one process per GPU at the same moment, and
+    eight concurrent rebuilds of the same object files hand a half-linked .so to whoever loads first."""
+    import fcntl
+
     srcs = _sources()
     if not force and _newer(LIB, srcs):
         return LIB
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _newer(LIB, srcs):  # another process built it while this one waited
+                return LIB
+            return _build_library_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_library_locked(verbose: bool) -> str:
     units = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))
              if f.endswith((".cu", ".cpp")) and not f.startswith("microbench")]
     # one nvcc process per translation unit, all at once (the pairtile instantiations dominate), then link
@@ -61,7 +76,10 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     for o, cmd, pr in procs:
         if pr.wait() != 0:
             raise subprocess.CalledProcessError(pr.returncode, cmd)
-    subprocess.run([_nvcc(), *ARCH, "-shared", "-o", LIB, *[o for o, _, _ in procs], "-lpthread", "-ldl"], check=True, cwd=CSRC)
+    # link to a temporary name and rename: a concurrent loader sees the old library or the new one, never a torso
+    tmp = LIB + ".tmp"
+    subprocess.run([_nvcc(), *ARCH, "-shared", "-o", tmp, *[o for o, _, _ in procs], "-lpthread", "-ldl"], check=True, cwd=CSRC)
+    os.replace(tmp, LIB)
     return LIB
 
 
