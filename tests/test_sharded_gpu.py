@@ -25,6 +25,7 @@ def test_shared_outputs_single_rank(kron, oracle_mod, n, d, dt):
     shared = [p.out_slab.data_ptr() + int(k) * s for k in keys[::2]]  # every other output goes through the scratch
     owner = np.zeros(len(shared), dtype=np.int32)
     st = torch.cuda.Stream()
+    torch.cuda.synchronize()  # the pointer arrays were built on torch's default stream; `st` does not wait for it
     kron.kronmult_batched_sharded(d, n, A, p.lda, i_, o_, w_, p.nb, shared, comm, owner=owner, dtype=dt, stream=st)
     st.synchronize()
     err = oracle_mod.rel_l2(p.out_slab.cpu().numpy(), expected)

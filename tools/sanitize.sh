@@ -2,11 +2,16 @@
 # compute-sanitizer passes over a slice of the GPU parity suite (memcheck / racecheck / synccheck).
 # usage (under gpurun): bash tools/sanitize.sh
 mkdir -p gpurun_out
-SEL='n4d5_ragged and (63 or 129) or n4d5_factor_layouts or every_kernel_family and (runs or shuffled) and not generic-8 or explicit_plan and 4-5 or edge_batches or unaligned or pairtile_ragged or pairtile_multipass and (7-6 or 10-6) or read_only_shared and (4-3 or 6-4 or 10-5) or pairtile_fp64 and (5-4 or 9-3 or 6-2) or sweep_envelope_fp64 and (4-3 or 2-5 or 4-2 or 4-6)'
+SEL='n4d5_ragged and (63 or 129) or n4d5_factor_layouts or every_kernel_family and (runs or shuffled) and not generic-8 or explicit_plan and 4-5 or edge_batches or unaligned or pairtile_ragged or pairtile_multipass and (7-6 or 10-6) or read_only_shared and (4-3 or 6-4 or 10-5) or pairtile_fp64 and (5-4 or 9-3 or 6-2) or sweep_envelope_fp64 and (4-3 or 2-5 or 4-2 or 4-6) or shared_outputs or host_buffer or asgard_batch'
 for tool in memcheck racecheck synccheck; do
+  # racecheck: the superseded wspec5 kernel (reachable only through kronmult_b200_force_path) is run separately below --
+  # its warp-to-warp mbarrier hand-off is not modelled by the tool and its 52 reports would hide everything else
+  EXTRA=""; [ $tool = racecheck ] && EXTRA=" and not wspec5"
   timeout -k 10 1500 compute-sanitizer --tool $tool --error-exitcode 77 --target-processes all \
-      python -m pytest tests/test_parity_gpu.py tests/test_sharded_gpu.py -q -m gpu -p no:cacheprovider -x -k "$SEL or shared_outputs or host_buffer or asgard_batch" > gpurun_out/sanitize_$tool.log 2>&1
+      python -m pytest tests/test_parity_gpu.py tests/test_sharded_gpu.py -q -m gpu -p no:cacheprovider -k "($SEL)$EXTRA" > gpurun_out/sanitize_$tool.log 2>&1
   echo "$tool rc=$?"; grep -E "ERROR SUMMARY|passed|failed|RACECHECK SUMMARY" gpurun_out/sanitize_$tool.log | tail -3
 done
-# which kernels the racecheck hazards are in
-grep -E "Race reported|hazard" gpurun_out/sanitize_racecheck.log | sed -E 's/.*in (void )?(kron::)?([a-z0-9_]+).*/\3/' | sort | uniq -c | sort -rn | head -20
+timeout -k 10 600 compute-sanitizer --tool racecheck --error-exitcode 77 --target-processes all \
+    python -m pytest tests/test_parity_gpu.py -q -m gpu -p no:cacheprovider -k "n4d5_ragged and 129 and wspec5 and float64" > gpurun_out/sanitize_racecheck_wspec5.log 2>&1
+echo "racecheck wspec5 rc=$?"; grep -E "passed|failed|RACECHECK SUMMARY" gpurun_out/sanitize_racecheck_wspec5.log | tail -2
+grep -oE "in kernel_[a-z0-9_]+\.cuh:[0-9]+" gpurun_out/sanitize_racecheck_wspec5.log | sort | uniq -c | sort -rn | head
