@@ -173,7 +173,9 @@ int kronmult_b200_force_path(int path);
  *         7: 1 = drop the dead intermediate from L2 with discard.global.L2 after a chunk's last pass (default 0).
  *         8: internal streams the chunks of knob 6 are spread over (default 3; 1 = the caller's stream only).
  *         9: 1 (default) = the one-thread-per-item kernels stage items of 128..512 bytes through shared memory with
- *            coalesced cp.async copies; 0 = every thread loads its own item (round-1 kernel). */
+ *            coalesced cp.async copies; 0 = every thread loads its own item (round-1 kernel).
+ *        10: 1 / 2 = single-precision n = 4, d = 5 runs on the half-warp-per-item kernel (kernel_symh.cuh, 8 / 12 CTAs
+ *            per SM); 0 (default, measured faster) = on the warp-per-item kernel of kernel_sym5.cuh. */
 int kronmult_b200_set_tuning(int knob, int value);
 
 #ifdef __cplusplus

@@ -22,9 +22,9 @@ import torch
 
 from . import build as _build
 
-PATH_AUTO, PATH_GENERIC, PATH_TINY, PATH_REGTILE, PATH_DMMA, PATH_WSPEC, PATH_WSPEC5, PATH_PAIRTILE, PATH_SYM5 = 0, 1, 2, 3, 4, 5, 6, 7, 8
+PATH_AUTO, PATH_GENERIC, PATH_TINY, PATH_REGTILE, PATH_DMMA, PATH_WSPEC, PATH_WSPEC5, PATH_PAIRTILE, PATH_SYM5, PATH_SYM4 = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 PATHS = {"auto": PATH_AUTO, "generic": PATH_GENERIC, "tiny": PATH_TINY, "regtile": PATH_REGTILE, "dmma": PATH_DMMA,
-         "wspec": PATH_WSPEC, "wspec5": PATH_WSPEC5, "pairtile": PATH_PAIRTILE, "sym5": PATH_SYM5}
+         "wspec": PATH_WSPEC, "wspec5": PATH_WSPEC5, "pairtile": PATH_PAIRTILE, "sym5": PATH_SYM5, "sym4": PATH_SYM4}
 
 # every symbol include/kronmult_b200.h declares (tests/test_abi.py checks the header against this)
 C_SYMBOLS = (

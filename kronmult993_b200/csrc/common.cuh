@@ -22,7 +22,8 @@ enum Path : int
     PATH_WSPEC5  = 6, // n = 4, d = 5: two items per step, split rows, double-buffered exchange
     PATH_PAIRTILE = 7, // compile-time (n, d), n x n register tiles, two factors per shared-memory round trip
     PATH_SYM5    = 8, // n = 4, d = 5: symmetric single-role kernel, one warp per item stream, in-place phases
-    PATH_LAST    = PATH_SYM5,
+    PATH_SYM4    = 9, // n = 4, d = 4: the same with a half-warp per item (two item streams per warp)
+    PATH_LAST    = PATH_SYM4,
 };
 
 __host__ __device__ constexpr int ipow(int b, int e)

@@ -17,6 +17,7 @@
 #include "kernel_wspec.cuh"
 #include "kernel_wspec5.cuh"
 #include "kernel_sym5.cuh"
+#include "kernel_symh.cuh"
 #include "kernel_pairtile.cuh"
 #include "kernel_pairpass.cuh"
 
@@ -333,6 +334,11 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
         e = run_sym5<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
         return e == cudaErrorNotSupported ? cudaErrorInvalidValue : e;
     }
+    if (force == PATH_SYM4)
+    {
+        e = run_sym4<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path, true);
+        return e == cudaErrorNotSupported ? cudaErrorInvalidValue : e;
+    }
     if (force == PATH_PAIRTILE)
     {
         e = run_pairtile<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches);
@@ -366,6 +372,8 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
             e = run_generic<T>(di, d, n, A, lda, in, out, nb, st, d - remaining, scratch, const_in);
         if (e != cudaErrorNotSupported) return e;
     }
+    e = run_sym4<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
+    if (e != cudaErrorNotSupported) return e;
     e = run_sym5<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
     if (e != cudaErrorNotSupported) return e;
     e = run_wspec<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path);
@@ -572,6 +580,7 @@ int kronmult_b200_set_tuning(int knob, int value)
     if (knob == 7) { kron::multipass_discard().store(value ? 1 : 0); return 0; }
     if (knob == 8 && value >= 1 && value <= 4) { kron::multipass_streams().store(value); return 0; }
     if (knob == 9) { kron::g_tiny_staged.store(value ? 1 : 0); return 0; }
+    if (knob == 10 && value >= 0 && value <= 2) { kron::g_symh_f32_d5.store(value); return 0; }
     return (int)cudaErrorInvalidValue;
 }
 int kronmult_b200_force_path(int path)

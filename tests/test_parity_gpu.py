@@ -87,7 +87,7 @@ def test_sweep_envelope_fp32(kron, oracle_mod, n, d):
 
 
 @pytest.mark.parametrize("path,n,d", [("tiny", 2, 2), ("tiny", 4, 2), ("tiny", 3, 2), ("tiny", 9, 1),
-                                      ("regtile", 4, 4), ("regtile", 4, 5), ("regtile", 4, 6), ("wspec", 4, 5), ("wspec", 4, 6), ("wspec5", 4, 5), ("sym5", 4, 5),
+                                      ("regtile", 4, 4), ("regtile", 4, 5), ("regtile", 4, 6), ("wspec", 4, 5), ("wspec", 4, 6), ("wspec5", 4, 5), ("sym5", 4, 5), ("sym4", 4, 4),
                                       ("generic", 4, 5), ("generic", 2, 2), ("generic", 8, 4)])
 @pytest.mark.parametrize("alias,kw", [("distinct", {}), ("runs", dict(items_per_output=32)),
                                       ("shuffled", dict(items_per_output=5)), ("ref", dict(nb_distinct=1))])
@@ -109,6 +109,23 @@ def test_n4d5_ragged_batches(kron, oracle_mod, nb, dt, path):
         hp = batch.make_problem(5, 4, nb, dt, "cpu", seed=nb, alias=alias, lda=6, **kw).to_host()
         _check(kron, oracle_mod, hp, path)
         assert kron.last_path() == path
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("nb", [1, 2, 3, 31, 32, 33, 64, 127, 129, 300, 4097, 70000])
+@pytest.mark.parametrize("d", [4, 5])
+def test_n4_half_warp_streams(kron, oracle_mod, nb, dt, d):
+    """n = 4, d = 4 (and d = 5 in single precision): two item streams per warp (half-warps) -- odd counts, one item, an
+    empty second stream, runs that straddle the streams, and every factor-staging route."""
+    if d == 5 and (dt == torch.float64 or nb > 5000):
+        pytest.skip("the half-warp kernel covers d = 5 in single precision only")
+    for alias, kw, mat in (("runs", dict(items_per_output=7), dict(lda=6)), ("distinct", {}, dict()),
+                           ("runs", dict(items_per_output=32), dict(matrices="asgard")),
+                           ("ref", dict(nb_distinct=3), dict(matrices="reftest")), ("runs", dict(items_per_output=5), dict(lda=8)),
+                           ("runs", dict(items_per_output=4), dict(misalign=1))):
+        hp = batch.make_problem(d, 4, nb, dt, "cpu", seed=nb, alias=alias, **kw, **mat).to_host()
+        _check(kron, oracle_mod, hp, "sym4")  # forcing the path reaches the d = 5 variant whatever knob 10 says
+        assert kron.last_path() == "sym4"
 
 
 @pytest.mark.parametrize("path", ["sym5", "wspec5"])
