@@ -42,13 +42,13 @@
 namespace kron
 {
 
-template<typename T, int WARPS_>
+template<typename T, int WARPS_, int NST_ = 2>
 struct Sym5
 {
     static constexpr int D       = 5;
     static constexpr int N       = 1024;
     static constexpr int WARPS   = WARPS_;                            // item streams (warps) per CTA
-    static constexpr int NST     = 2;                                 // TMA ring stages per stream
+    static constexpr int NST     = NST_;                              // TMA ring stages per stream (items staged NST-1 ahead)
     static constexpr int MSTR    = D * 16;                            // an item's factors: 5 column-major 4x4 blocks
     static constexpr int STG     = N + (sizeof(T) == 8 ? 80 : 96);    // ring stage (vector, then factors): k * 128 bytes
     static constexpr int THREADS = 32 * WARPS;
@@ -80,11 +80,11 @@ __device__ __forceinline__ void tile16_apply_cm(T (&x)[16], const T (&m)[16])
 
 // VAR bit 0: phase A on single columns (two half-passes of 16 values per lane) instead of column pairs
 template<typename T, int WARPS, int MINB, int VAR>
-__global__ void __launch_bounds__(Sym5<T, WARPS>::THREADS, MINB)
+__global__ void __launch_bounds__(Sym5<T, WARPS, ((VAR & 8) ? 3 : 2)>::THREADS, MINB)
 kron_sym5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T *const *__restrict__ out,
                  const int lda, const int nb, const long long items_per_warp)
 {
-    using C = Sym5<T, WARPS>;
+    using C = Sym5<T, WARPS, ((VAR & 8) ? 3 : 2)>;
     using P = typename V2<T>::type;
     constexpr int D = 5, N = C::N, NST = C::NST, STG = C::STG;
     constexpr unsigned S = sizeof(T);
@@ -243,22 +243,31 @@ kron_sym5_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T *c
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     stage_item(true, 0, pr_in(0), pr_ap(0));
+    if constexpr (NST == 3) { if (cnt > 1) stage_item(true, 1, pr_in(1), pr_ap(1)); }
     cp_async_commit();
-    if (cnt > 1) l2_pull(pr_in(1));
+    if constexpr (NST == 2) { if (cnt > 1) l2_pull(pr_in(1)); }
 
     for (int s = 0; s < cnt; ++s)
     {
-        const int st = s & 1;
+        const int st = (NST == 2) ? (s & 1) : (s % 3);
         // every cp.async group committed in earlier steps is complete: the pointers of items s+1 and s+2 and any
         // element-wise copies of item s (issued a whole step ago)
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp(); // ... and visible to all lanes; every read of stage st^1 (item s-1) and ring slot (s+3)&3 is done
         // stage st^1 was last read by this warp in step s-1
-        if (s + 1 < cnt) stage_item(true, st ^ 1, pr_in(s + 1), pr_ap(s + 1));
-        if constexpr ((VAR & 4) == 0) { if (s + 2 < cnt) l2_pull(pr_in(s + 2)); }
+        if constexpr (NST == 2)
+        {
+            if (s + 1 < cnt) stage_item(true, st ^ 1, pr_in(s + 1), pr_ap(s + 1));
+            if constexpr ((VAR & 4) == 0) { if (s + 2 < cnt) l2_pull(pr_in(s + 2)); }
+        }
+        else
+        {
+            // three stages: item s+2 goes into the stage item s-1 has just left
+            if (s + 2 < cnt) stage_item(true, (s + 2) % 3, pr_in(s + 2), pr_ap(s + 2));
+        }
         fetch_ptrs(s + 3);
         cp_async_commit();
-        mbar_wait_a(b_full + 8 * st, (unsigned)(s >> 1) & 1u);
+        mbar_wait_a(b_full + 8 * st, (unsigned)((NST == 2) ? (s >> 1) : (s / 3)) & 1u);
 
         T *stage    = IN + st * STG;
         const T *Mq = stage + N; // factors 0..4, column-major 4x4 blocks
@@ -424,7 +433,7 @@ template<typename T, int WARPS, int MINB, int VAR>
 static cudaError_t launch_sym5(int sms, const T *const *A, int lda, T *const *in, T *const *out, int nb,
                                cudaStream_t st, std::atomic<long long> &launches)
 {
-    using C  = Sym5<T, WARPS>;
+    using C  = Sym5<T, WARPS, ((VAR & 8) ? 3 : 2)>;
     auto kfn = kron_sym5_kernel<T, WARPS, MINB, VAR>;
     int ctas_per_sm = 0;
     cudaError_t e = kernel_setup(kfn, C::THREADS, C::SMEM, ctas_per_sm);
@@ -471,6 +480,8 @@ static cudaError_t run_sym5(int sms, int d, int n, const T *const *A, int lda, T
         case 12: e = KRON_SYM5(1, 12, 2); break;
         case 13: e = KRON_SYM5(1, 12, 6); break;
         case 14: e = KRON_SYM5(4, 2, 2); break;
+        case 16: e = KRON_SYM5(1, 8, 8); break;  // three-stage ring
+        case 17: e = KRON_SYM5(1, 8, 4); break;  // no L2 pull
 #endif
         }
     }
