@@ -548,6 +548,163 @@ static cudaError_t launch_dmma8_rows2(int sms, int d, long long N, const double 
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// n = 8, d = 2 and 3 (64- and 512-element vectors): one WARP per item, everything in registers.
+// ncu on the pair-tile kernel these shapes used (profiles/ncu_pairtile_small_r02.md): n = 8, d = 3 is shared-memory-
+// bound with a third of its wavefronts being bank-conflict replays, the d = 2 items are instruction-bound.  With
+// the chained DMMA of the d = 4 kernel a warp needs no shared memory for the two fastest factors at all: a lane
+// loads its two adjacent elements of every 64-element slice straight from global memory (one coalesced 512-byte
+// request per slice), 4 DMMAs contract the slice's two indices and leave the result on the positions it was loaded
+// from.  d = 3: the remaining factor combines the eight slices with coefficients that are uniform over the warp --
+// its 64 entries travel through 512 bytes of shared memory per warp (cp.async one item ahead, broadcast 128-bit
+// loads), 128 DFMA per lane.  Runs of equal output pointers are summed in the 2 (16) result registers; the flush is
+// two REDG per lane and slice on adjacent elements (sector-complete over the warp).  Data of item s+1 is in flight
+// in registers while item s is computed; pointers travel two items ahead.
+inline std::atomic<int> &dmma8s_enabled() { static std::atomic<int> v{1}; return v; } // knob 11
+
+template<int D>
+__global__ void __launch_bounds__(128, (D == 2) ? 6 : 3)
+kron_dmma8s_kernel(const double *const *__restrict__ A, double *const *__restrict__ in, double *const *__restrict__ out,
+                   const int lda, const int nb, const long long items_per_warp)
+{
+    constexpr int SL = (D == 2) ? 1 : 8; // 64-element slices per item
+    __shared__ __align__(16) double F0s[4][2][64]; // d = 3: factor 0 of items s, s+1 per warp (column-major 8 x 8)
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const long long lane_off0 = g + (long long)(2 * q) * lda;
+    const int epos = g * 8 + 2 * q; // my two adjacent elements of a slice
+
+    const long long k0 = ((long long)blockIdx.x * 4 + w) * items_per_warp;
+    if (k0 >= nb) return;
+    const int cnt = (int)((k0 + items_per_warp <= nb) ? items_per_warp : (nb - k0));
+
+    struct Ptrs { const double *ip; double *op; const double *ap[D]; };
+    auto load_ptrs = [&](int s, Ptrs &p) {
+        if (s >= cnt) { p.ip = nullptr; p.op = nullptr; return; }
+        const long long k = k0 + s;
+        p.ip = in[k]; p.op = out[k];
+#pragma unroll
+        for (int j = 0; j < D; ++j) p.ap[j] = A[k * D + j];
+    };
+    struct Data { double2 x[SL]; double a[4]; };
+    auto load_data = [&](const Ptrs &p, Data &dt, int slot) {
+        if (!p.ip) return;
+        if (aligned16(p.ip))
+        {
+#pragma unroll
+            for (int h = 0; h < SL; ++h) dt.x[h] = __ldg(reinterpret_cast<const double2 *>(p.ip + h * 64 + epos));
+        }
+        else
+        {
+#pragma unroll
+            for (int h = 0; h < SL; ++h) dt.x[h] = make_double2(__ldg(p.ip + h * 64 + epos), __ldg(p.ip + h * 64 + epos + 1));
+        }
+        // fragments of the two fastest factors: M[g][2q], M[g][2q+1]
+        dt.a[0] = __ldg(p.ap[D - 2] + lane_off0); dt.a[1] = __ldg(p.ap[D - 2] + lane_off0 + lda);
+        dt.a[2] = __ldg(p.ap[D - 1] + lane_off0); dt.a[3] = __ldg(p.ap[D - 1] + lane_off0 + lda);
+        if constexpr (D == 3)
+        {
+            // factor 0 -> shared memory, column-major compact: element (r, c) at c*8 + r; two elements per lane
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(&F0s[w][slot][0]);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+            {
+                const int e = lane + 32 * i, r = e & 7, c = e >> 3;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa + e * 8), "l"(p.ap[0] + r + (long long)c * lda) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    Ptrs p_cur, p_nxt, p_nx2;
+    Data d_cur, d_nxt;
+    load_ptrs(0, p_cur);
+    load_ptrs(1, p_nxt);
+    load_data(p_cur, d_cur, 0);
+
+    double acc[SL][2];
+#pragma unroll
+    for (int h = 0; h < SL; ++h) acc[h][0] = acc[h][1] = 0.0;
+
+    for (int s = 0; s < cnt; ++s)
+    {
+        load_ptrs(s + 2, p_nx2);
+        load_data(p_nxt, d_nxt, (s + 1) & 1); // item s+1 in flight while item s is computed
+        if constexpr (D == 3)
+        {
+            asm volatile("cp.async.wait_group 1;" ::: "memory"); // factor 0 of item s has landed (item s+1's may be pending)
+            __syncwarp();
+        }
+        double z[SL][2];
+#pragma unroll
+        for (int h = 0; h < SL; ++h)
+        {
+            double y0, y1;
+            dmma884(y0, y1, d_cur.a[2], d_cur.x[h].x, 0.0, 0.0);
+            dmma884(y0, y1, d_cur.a[3], d_cur.x[h].y, y0, y1);
+            if constexpr (D == 2)
+            {
+                // the second product accumulates straight onto the run sum (C operand)
+                dmma884(acc[0][0], acc[0][1], d_cur.a[0], y0, acc[0][0], acc[0][1]);
+                dmma884(acc[0][0], acc[0][1], d_cur.a[1], y1, acc[0][0], acc[0][1]);
+            }
+            else
+            {
+                dmma884(z[h][0], z[h][1], d_cur.a[0], y0, 0.0, 0.0);
+                dmma884(z[h][0], z[h][1], d_cur.a[1], y1, z[h][0], z[h][1]);
+            }
+        }
+        if constexpr (D == 3)
+        {
+            const double *F = &F0s[w][s & 1][0];
+#pragma unroll
+            for (int h = 0; h < 8; ++h)
+            {
+                double f[8]; // column h of factor 0: F0(h', h), h' = 0..7
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                {
+                    const double2 v = *reinterpret_cast<const double2 *>(F + h * 8 + 2 * c);
+                    f[2 * c] = v.x; f[2 * c + 1] = v.y;
+                }
+#pragma unroll
+                for (int hp = 0; hp < 8; ++hp)
+                {
+                    acc[hp][0] = fma(f[hp], z[h][0], acc[hp][0]);
+                    acc[hp][1] = fma(f[hp], z[h][1], acc[hp][1]);
+                }
+            }
+            __syncwarp(); // every lane has read slot s & 1 before item s+2's factor is copied into it
+        }
+        if (p_nxt.op != p_cur.op) // end of the run of equal output pointers (also the last item: p_nxt.op is null)
+        {
+#pragma unroll
+            for (int h = 0; h < SL; ++h)
+            {
+                red_add(p_cur.op + h * 64 + epos, acc[h][0]);
+                red_add(p_cur.op + h * 64 + epos + 1, acc[h][1]);
+                acc[h][0] = acc[h][1] = 0.0;
+            }
+        }
+        p_cur = p_nxt; p_nxt = p_nx2;
+        d_cur = d_nxt;
+    }
+}
+
+template<int D>
+static cudaError_t launch_dmma8s(int sms, const double *const *A, int lda, double *const *in, double *const *out, int nb,
+                                 cudaStream_t st, std::atomic<long long> &launches)
+{
+    const long long warps = (long long)sms * ((D == 2) ? 6 : 3) * 4;
+    long long ipw = ((long long)nb + warps - 1) / warps;
+    if (ipw > 64) ipw = (ipw + 31) / 32 * 32;
+    const long long nw   = ((long long)nb + ipw - 1) / ipw;
+    const long long grid = (nw + 3) / 4;
+    kron_dmma8s_kernel<D><<<(int)grid, 128, 0, st>>>(A, in, out, lda, nb, ipw);
+    launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
 // cudaErrorNotSupported when the shape or type is outside the family.
 // d = 5 returns cudaSuccess after pass A with *remaining = 1: the caller applies factor 0 (generic pass).
 template<typename T>
@@ -562,6 +719,12 @@ static cudaError_t run_dmma(int sms, int d, int n, const T *const *A, int lda, T
         {
             last_path = "dmma";
             return launch_dmma84(sms, A, lda, in, out, nb, st, launches);
+        }
+        if (n == 8 && (d == 2 || d == 3) && dmma8s_enabled().load(std::memory_order_relaxed))
+        {
+            last_path = "dmma";
+            return d == 2 ? launch_dmma8s<2>(sms, A, lda, in, out, nb, st, launches)
+                          : launch_dmma8s<3>(sms, A, lda, in, out, nb, st, launches);
         }
         if (n == 8 && (d == 5 || d == 6))
         {

@@ -597,6 +597,7 @@ int kronmult_b200_set_tuning(int knob, int value)
     if (knob == 8 && value >= 1 && value <= 4) { kron::multipass_streams().store(value); return 0; }
     if (knob == 9) { kron::g_tiny_staged.store(value ? 1 : 0); return 0; }
     if (knob == 10 && value >= 0 && value <= 2) { kron::g_symh_f32_d5.store(value); return 0; }
+    if (knob == 11) { kron::dmma8s_enabled().store(value ? 1 : 0); return 0; }
     return (int)cudaErrorInvalidValue;
 }
 int kronmult_b200_force_path(int path)
