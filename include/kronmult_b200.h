@@ -172,8 +172,9 @@ int kronmult_b200_force_path(int path);
  *            the default: 32 MiB for routes of three or more passes, where it measured 29 % faster, else 0).
  *         7: 1 = drop the dead intermediate from L2 with discard.global.L2 after a chunk's last pass (default 0).
  *         8: internal streams the chunks of knob 6 are spread over (default 3; 1 = the caller's stream only).
- *         9: 1 (default) = the one-thread-per-item kernels stage items of 128..512 bytes through shared memory with
- *            coalesced cp.async copies; 0 = every thread loads its own item (round-1 kernel).
+ *         9: 1 (default) = the one-thread-per-item kernels stage items of 128 / 256 / 512 bytes through shared memory with
+ *            coalesced 16-byte cp.async copies, and five more fp64 shapes with element-wise copies; 2 = the former
+ *            only; 0 = every thread loads its own item (round-1 kernel).
  *        10: 1 / 2 = single-precision n = 4, d = 5 runs on the half-warp-per-item kernel (kernel_symh.cuh, 8 / 12 CTAs
  *            per SM); 0 (default, measured faster) = on the warp-per-item kernel of kernel_sym5.cuh.
  *        11: 1 (default) = double-precision n = 8, d = 2 / 3 on the warp-per-item DMMA kernel; 0 = pair-tile kernel. */

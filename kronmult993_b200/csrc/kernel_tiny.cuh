@@ -374,4 +374,170 @@ kron_tiny_staged_kernel(const T *const *__restrict__ A, T *const *__restrict__ i
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Element-wise staged variant for every other item size (n^d * sizeof(T) not 128 / 256 / 512 bytes: n = 3, 5, 6, 7, 9, 10
+// ...): the same idea with 4- / 8-byte cp.async copies.  For item j of the warp the 32 lanes copy elements lane,
+// lane + 32, ... (one warp instruction = up to 256 contiguous bytes of ONE item instead of 32 scattered pieces), the
+// d factors of an item are copied as one flattened run of d*n*n elements (any lda).  Rows are an ODD number of
+// elements apart, so a lane's reads of its own row are bank-conflict free without any permutation.
+template<typename T, int n, int d>
+struct TinyEStaged
+{
+    static constexpr int N     = ipow(n, d);
+    static constexpr int S     = (int)sizeof(T);
+    static constexpr int FE    = d * n * n;                   // factor elements per item
+    static constexpr int VP    = N | 1;                       // row pitches in elements (odd)
+    static constexpr int FP    = FE | 1;
+    static constexpr int WARPS = 2;
+    static constexpr int WBYTES = ((32 * (VP + FP) * S + 32 * d * 8 + 32 * 8) + 15) / 16 * 16;
+    static constexpr int SMEM  = WARPS * WBYTES;
+    // Measured on B200 (tools/tiny_session.sh, knob 9 = 1 vs 2): the many small copies pay only where the plain kernel's
+    // per-thread loads were worst -- fp64 n = 8, 9 with d = 1 (0.70 -> 0.79, 0.52 -> 0.68: the factor is larger than the
+    // vector), n = 3, d = 3 (0.64 -> 0.70), n = 5, d = 2 (0.60 -> 0.64), n = 3, d = 4; everywhere else (all of fp32,
+    // n = 6, 7, 10) the plain kernel is faster by up to 2x, so those shapes keep it.
+    static constexpr bool LISTED = sizeof(T) == 8 && ((d == 1 && (n == 8 || n == 9)) || (n == 3 && (d == 3 || d == 4)) || (n == 5 && d == 2));
+    static constexpr bool OK   = LISTED && !TinyStaged<T, n, d>::OK && SMEM <= 200 * 1024;
+};
+
+template<typename T, int n, int d>
+__global__ void __launch_bounds__(TinyEStaged<T, n, d>::WARPS * 32)
+kron_tiny_estaged_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T *const *__restrict__ out, int lda,
+                         int nb)
+{
+    using C = TinyEStaged<T, n, d>;
+    constexpr int N = C::N, S = C::S, FE = C::FE, VP = C::VP, FP = C::FP;
+    extern __shared__ __align__(16) unsigned char tiny_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char *wb = tiny_smem + warp * C::WBYTES;
+    T *vbuf           = reinterpret_cast<T *>(wb);                         // [32][VP]
+    T *fbuf           = vbuf + 32 * VP;                                    // [32][FP]
+    const T **ptab    = reinterpret_cast<const T **>(wb + ((32 * (VP + FP) * S + 7) / 8) * 8); // [32 * d] factor pointers
+    const T **itab    = ptab + 32 * d;                                     // [32] vector pointers
+
+    const long long k0 = ((long long)blockIdx.x * C::WARPS + warp) * 32;
+    if (k0 >= nb) return;                                                  // whole warp
+    long long k      = k0 + lane;
+    const bool valid = k < nb;
+    if (!valid) k = nb - 1; // a duplicate of the last item, dropped at the flush (the warp stays converged)
+
+    itab[lane] = in[k];
+#pragma unroll
+    for (int i = 0; i < d; ++i)
+    {
+        const long long e = k0 * d + lane + 32 * i;
+        ptab[lane + 32 * i] = A[e < (long long)nb * d ? e : (long long)nb * d - 1];
+    }
+    __syncwarp();
+    const unsigned vs = (unsigned)__cvta_generic_to_shared(vbuf), fs = (unsigned)__cvta_generic_to_shared(fbuf);
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j)
+    {
+        const T *src = itab[j];
+#pragma unroll
+        for (int i = 0; i < (N + 31) / 32; ++i)
+        {
+            const int e = lane + 32 * i;
+            if (e < N)
+            {
+                if constexpr (S == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(vs + (j * VP + e) * 8), "l"(src + e) : "memory");
+                else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(vs + (j * VP + e) * 4), "l"(src + e) : "memory");
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < (FE + 31) / 32; ++i)
+        {
+            const int e = lane + 32 * i; // element e = factor e / n^2, column (e % n^2) / n, row e % n
+            if (e < FE)
+            {
+                const int f = e / (n * n), rc = e - f * (n * n), c = rc / n, r = rc - c * n;
+                const T *g = ptab[j * d + f] + r + (long long)c * lda;
+                if constexpr (S == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(fs + (j * FP + e) * 8), "l"(g) : "memory");
+                else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(fs + (j * FP + e) * 4), "l"(g) : "memory");
+            }
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    T *o = out[k]; // in flight while the copies land
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+
+    T v[N];
+    {
+        const T *row = vbuf + lane * VP;
+#pragma unroll
+        for (int e = 0; e < N; ++e) v[e] = row[e];
+    }
+#pragma unroll
+    for (int j = d - 1; j >= 0; --j)
+    {
+        T m[n * n]; // m[c*n + r] = M(r, c)
+        const T *row = fbuf + lane * FP + j * n * n;
+#pragma unroll
+        for (int e = 0; e < n * n; ++e) m[e] = row[e];
+        const int St = ipow(n, d - 1 - j); // stride of the index factor j acts on
+#pragma unroll
+        for (int f = 0; f < N / n; ++f)
+        {
+            const int hi   = f / St;
+            const int lo   = f - hi * St;
+            const int base = hi * St * n + lo;
+            T x[n];
+#pragma unroll
+            for (int kk = 0; kk < n; ++kk) x[kk] = v[base + kk * St];
+#pragma unroll
+            for (int i = 0; i < n; ++i)
+            {
+                T dot = T(0);
+#pragma unroll
+                for (int kk = 0; kk < n; ++kk) dot += x[kk] * m[kk * n + i];
+                v[base + i * St] = dot;
+            }
+        }
+    }
+
+    // flush through the (now free) staging area: same scheme as kron_tiny_kernel
+    {
+        constexpr int CH     = N < 32 ? N : 32;      // elements per round
+        constexpr int ROUNDS = (N + CH - 1) / CH;
+        constexpr int PITCH  = CH | 1;               // odd pitch: conflict-free rows
+        constexpr int G      = 32 / CH;              // lane groups
+        constexpr int SEG    = (32 + G - 1) / G;     // consecutive items per group
+        static_assert(32 * PITCH * S + 8 + 32 * 8 <= C::WBYTES, "the flush buffer fits the warp's staging area");
+        T *sv    = reinterpret_cast<T *>(wb);
+        T **sout = reinterpret_cast<T **>(wb + ((32 * PITCH * S + 7) / 8) * 8);
+        __syncwarp(); // every lane has read its rows (vector and factors)
+        sout[lane] = valid ? o : nullptr;
+        const int g = lane / CH, i = lane - g * CH;
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r)
+        {
+            if (r > 0) __syncwarp();
+#pragma unroll
+            for (int e = 0; e < CH; ++e)
+                if (r * CH + e < N) sv[lane * PITCH + e] = v[r * CH + e];
+            __syncwarp();
+            if (g < G && r * CH + i < N)
+            {
+                T sum  = T(0);
+                T *cur = nullptr;
+#pragma unroll 4
+                for (int t = 0; t < SEG; ++t)
+                {
+                    const int item = g * SEG + t;
+                    if (item >= 32) break;
+                    T *oo = sout[item];
+                    if (oo != cur)
+                    {
+                        if (cur) red_add(cur + r * CH + i, sum);
+                        cur = oo;
+                        sum = T(0);
+                    }
+                    sum += sv[item * PITCH + i];
+                }
+                if (cur) red_add(cur + r * CH + i, sum);
+            }
+        }
+    }
+}
+
 } // namespace kron

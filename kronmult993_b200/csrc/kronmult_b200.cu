@@ -275,6 +275,22 @@ static cudaError_t launch_tiny(const T *const *A, int lda, T *const *in, T *cons
             return cudaGetLastError();
         }
     }
+    using CE = TinyEStaged<T, n, d>;
+    if constexpr (CE::OK)
+    {
+        if (g_tiny_staged.load(std::memory_order_relaxed) == 1)
+        {
+            auto kfn = kron_tiny_estaged_kernel<T, n, d>;
+            cudaError_t e = kernel_setup(kfn, CE::SMEM);
+            if (e != cudaSuccess) return e;
+            const int per  = CE::WARPS * 32;
+            const int grid = (nb + per - 1) / per;
+            kfn<<<grid, per, CE::SMEM, st>>>(A, in, out, lda, nb);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            t_last_path = "tiny";
+            return cudaGetLastError();
+        }
+    }
     const int threads = 128;
     const int grid    = (nb + threads - 1) / threads;
     kron_tiny_kernel<T, n, d><<<grid, threads, 0, st>>>(A, in, out, lda, nb);
@@ -595,7 +611,7 @@ int kronmult_b200_set_tuning(int knob, int value)
     if (knob == 6 && value >= -1 && value <= 4096) { kron::multipass_chunk_mib().store(value); return 0; }
     if (knob == 7) { kron::multipass_discard().store(value ? 1 : 0); return 0; }
     if (knob == 8 && value >= 1 && value <= 4) { kron::multipass_streams().store(value); return 0; }
-    if (knob == 9) { kron::g_tiny_staged.store(value ? 1 : 0); return 0; }
+    if (knob == 9 && value >= 0 && value <= 2) { kron::g_tiny_staged.store(value); return 0; } // 2: chunked variant only
     if (knob == 10 && value >= 0 && value <= 2) { kron::g_symh_f32_d5.store(value); return 0; }
     if (knob == 11) { kron::dmma8s_enabled().store(value ? 1 : 0); return 0; }
     return (int)cudaErrorInvalidValue;
