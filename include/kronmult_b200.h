@@ -177,7 +177,8 @@ int kronmult_b200_force_path(int path);
  *            only; 0 = every thread loads its own item (round-1 kernel).
  *        10: 1 / 2 = single-precision n = 4, d = 5 runs on the half-warp-per-item kernel (kernel_symh.cuh, 8 / 12 CTAs
  *            per SM); 0 (default, measured faster) = on the warp-per-item kernel of kernel_sym5.cuh.
- *        11: 1 (default) = double-precision n = 8, d = 2 / 3 on the warp-per-item DMMA kernel; 0 = pair-tile kernel. */
+ *        11: warp-per-item DMMA kernel (n = 5..8, d = 2, 3, both precisions): 1 (default) = the shapes where it measured
+ *            faster, 2 = every shape it supports, 0 = off (tiny / pair-tile kernels). */
 int kronmult_b200_set_tuning(int knob, int value);
 
 #ifdef __cplusplus

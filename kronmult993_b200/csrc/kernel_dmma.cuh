@@ -38,9 +38,147 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
         : "d"(a), "d"(b), "d"(c0), "d"(c1));
 }
 
+// volatile twin: keeps the issue order written in the source (the chains below are interleaved on purpose; left to
+// itself the compiler re-serialises them chain by chain to save registers)
+__device__ __forceinline__ void dmma884v(double &d0, double &d1, double a, double b, double c0, double c1)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+                 : "=d"(d0), "=d"(d1)
+                 : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
+
+// Two chained mode products (factor U on the contracted index of the B fragment, then factor V on the other one) on NS
+// independent 8 x 8 slices at once, stage by stage, so that ptxas can interleave the NS dependency chains: one chain is
+// four back-to-back DEPENDENT DMMAs, and a warp that issues them slice after slice (load, 4 DMMAs, store, next slice)
+// keeps the FP64 tensor pipe idle for most of each DMMA's latency -- ncu on the persistent n = 8, d = 6 kernel showed the
+// pipe 38 % busy with exactly that instruction order (profiles/ncu_dmma_l2_r02.md).
+template<int NS>
+__device__ __forceinline__ void dmma_pair(double u0, double u1, double v0, double v1, const double (&x0)[NS],
+                                          const double (&x1)[NS], double (&z0)[NS], double (&z1)[NS])
+{
+    double y0[NS], y1[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) dmma884v(y0[i], y1[i], u0, x0[i], 0.0, 0.0);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) dmma884v(y0[i], y1[i], u1, x1[i], y0[i], y1[i]);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) dmma884v(z0[i], z1[i], v0, y0[i], 0.0, 0.0);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) dmma884v(z0[i], z1[i], v1, y1[i], z0[i], z1[i]);
+}
+// the same with the second product accumulating onto (c0, c1) -- the running sum of a run of equal output pointers
+template<int NS>
+__device__ __forceinline__ void dmma_pair_acc(double u0, double u1, double v0, double v1, const double (&x0)[NS],
+                                              const double (&x1)[NS], double (&c0)[NS], double (&c1)[NS])
+{
+    double y0[NS], y1[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) dmma884v(y0[i], y1[i], u0, x0[i], 0.0, 0.0);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) dmma884v(y0[i], y1[i], u1, x1[i], y0[i], y1[i]);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) dmma884v(c0[i], c1[i], v0, y0[i], c0[i], c1[i]);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) dmma884v(c0[i], c1[i], v1, y1[i], c0[i], c1[i]);
+}
+
 // 16-byte-chunk swizzle of the exchange buffer: slice h = i0*8+i1 holds 64 contiguous doubles
 // (32 chunks); chunk index is XORed with ((i0&1)<<2 | i1>>1).
 __device__ __forceinline__ int dmma_sigma(int h) { return (((h >> 3) & 1) << 2) | ((h >> 1) & 3); }
+
+// Phase 2 of the n = 8 kernels on a chunk-swizzled 4096-element tile: warp w owns the P2 slice pairs j = w*P2 .. and
+// contracts the two slow indices of the tile (rows h0 = 8g + 2q, h0 + 1), GJ slice pairs (2 GJ chains) at a time.
+// acc[jj][s + 2t] = Out[i0 = g][i1 = 2q + s][f = 2j + t]: the products accumulate onto the run sums.
+template<int P2, int GJ>
+__device__ __forceinline__ void dmma_phase2_acc(const double *__restrict__ Ec, int w, int g, int q, double u0, double u1,
+                                                double v0, double v1, double (&acc)[P2][4], int jbase = 0)
+{
+    const int h0 = g * 8 + 2 * q;
+    const int sg = ((g & 1) << 2) | q; // dmma_sigma(h0) == dmma_sigma(h0 + 1)
+#pragma unroll
+    for (int j0 = 0; j0 < P2; j0 += GJ)
+    {
+        double x0[2 * GJ], x1[2 * GJ], c0[2 * GJ], c1[2 * GJ];
+#pragma unroll
+        for (int i = 0; i < GJ; ++i)
+        {
+            const int j = jbase + w * P2 + j0 + i; // slices f = 2j, 2j+1
+            const double2 a0 = *reinterpret_cast<const double2 *>(Ec + h0 * 64 + ((j ^ sg) << 1));
+            const double2 a1 = *reinterpret_cast<const double2 *>(Ec + (h0 + 1) * 64 + ((j ^ sg) << 1));
+            x0[2 * i] = a0.x; x1[2 * i] = a1.x; x0[2 * i + 1] = a0.y; x1[2 * i + 1] = a1.y;
+            c0[2 * i] = acc[j0 + i][0]; c1[2 * i] = acc[j0 + i][1]; c0[2 * i + 1] = acc[j0 + i][2]; c1[2 * i + 1] = acc[j0 + i][3];
+        }
+        dmma_pair_acc<2 * GJ>(u0, u1, v0, v1, x0, x1, c0, c1);
+#pragma unroll
+        for (int i = 0; i < GJ; ++i)
+        {
+            acc[j0 + i][0] = c0[2 * i]; acc[j0 + i][1] = c1[2 * i]; acc[j0 + i][2] = c0[2 * i + 1]; acc[j0 + i][3] = c1[2 * i + 1];
+        }
+    }
+}
+// the same in place (pass A of the multi-pass routes: the tile goes back to memory afterwards)
+template<int P2, int GJ>
+__device__ __forceinline__ void dmma_phase2_inplace(double *__restrict__ Ec, int w, int g, int q, double u0, double u1,
+                                                    double v0, double v1)
+{
+    const int h0 = g * 8 + 2 * q;
+    const int sg = ((g & 1) << 2) | q;
+#pragma unroll
+    for (int j0 = 0; j0 < P2; j0 += GJ)
+    {
+        double x0[2 * GJ], x1[2 * GJ], z0[2 * GJ], z1[2 * GJ];
+#pragma unroll
+        for (int i = 0; i < GJ; ++i)
+        {
+            const int j = w * P2 + j0 + i;
+            const double2 a0 = *reinterpret_cast<const double2 *>(Ec + h0 * 64 + ((j ^ sg) << 1));
+            const double2 a1 = *reinterpret_cast<const double2 *>(Ec + (h0 + 1) * 64 + ((j ^ sg) << 1));
+            x0[2 * i] = a0.x; x1[2 * i] = a1.x; x0[2 * i + 1] = a0.y; x1[2 * i + 1] = a1.y;
+        }
+        dmma_pair<2 * GJ>(u0, u1, v0, v1, x0, x1, z0, z1);
+        // a lane rewrites exactly the two chunks it read: no other lane touches them in this phase
+#pragma unroll
+        for (int i = 0; i < GJ; ++i)
+        {
+            const int j = w * P2 + j0 + i;
+            *reinterpret_cast<double2 *>(Ec + h0 * 64 + ((j ^ sg) << 1))       = make_double2(z0[2 * i], z0[2 * i + 1]);
+            *reinterpret_cast<double2 *>(Ec + (h0 + 1) * 64 + ((j ^ sg) << 1)) = make_double2(z1[2 * i], z1[2 * i + 1]);
+        }
+    }
+}
+// Phase 1 on a tile in shared memory: warp w owns the T1 slices h = w*T1 .., contracts their two fast indices G1 slices
+// at a time and rewrites them chunk-swizzled in place.  `gsrc` != nullptr: the tile is read from global memory instead
+// (vectors that are not 16-byte aligned cannot come by TMA).
+template<int T1, int G1>
+__device__ __forceinline__ void dmma_phase1_inplace(double *__restrict__ Ec, const double *__restrict__ gsrc, int w, int g,
+                                                    int q, double u0, double u1, double v0, double v1)
+{
+#pragma unroll
+    for (int t0 = 0; t0 < T1; t0 += G1)
+    {
+        double x0[G1], x1[G1], z0[G1], z1[G1];
+#pragma unroll
+        for (int i = 0; i < G1; ++i)
+        {
+            const int h = w * T1 + t0 + i;
+            if (!gsrc)
+            {
+                const double2 v = *reinterpret_cast<const double2 *>(Ec + h * 64 + g * 8 + 2 * q);
+                x0[i] = v.x; x1[i] = v.y;
+            }
+            else { x0[i] = __ldg(gsrc + h * 64 + g * 8 + 2 * q); x1[i] = __ldg(gsrc + h * 64 + g * 8 + 2 * q + 1); }
+        }
+        dmma_pair<G1>(u0, u1, v0, v1, x0, x1, z0, z1);
+        __syncwarp(); // every lane has read its chunks of these slices before they are rewritten
+#pragma unroll
+        for (int i = 0; i < G1; ++i)
+        {
+            const int h = w * T1 + t0 + i;
+            const int chunk16 = (4 * g + q) ^ dmma_sigma(h);
+            *reinterpret_cast<double2 *>(Ec + h * 64 + chunk16 * 2) = make_double2(z0[i], z1[i]);
+        }
+    }
+}
 
 struct Dmma84
 {
@@ -50,6 +188,8 @@ struct Dmma84
     static constexpr int T1      = 64 / WARPS;      // phase-1 slices per warp
     static constexpr int P2      = 32 / WARPS;      // phase-2 slice pairs per warp
     static constexpr int SMEM    = 2 * N * 8 + 32;  // two item slots + their mbarriers
+    static constexpr int G1      = 8;               // phase-1 slices a warp works on at once (independent DMMA chains)
+    static constexpr int G2      = 4;               // phase-2 slice pairs at once (two chains each)
 };
 
 // Items arrive by TMA: one elected thread fetches item k+1 with a single 32 KiB cp.async.bulk into the other slot
@@ -152,26 +292,7 @@ kron_dmma84_kernel(const double *const *__restrict__ A, double *const *__restric
         // ---------------- phase 1: factors 3 (index i3 = u) and 2 (index i2 = v), slice by slice, in place
         const bool vec = aligned16(ip_cur);
         mbar_wait(bar + cur, (unsigned)((k - k0) >> 1) & 1u);
-#pragma unroll
-        for (int tt = 0; tt < T1; ++tt)
-        {
-            const int h = w * T1 + tt;
-            double x0, x1;
-            if (vec)
-            {
-                const double2 v = *reinterpret_cast<const double2 *>(Ec + h * 64 + g * 8 + 2 * q);
-                x0 = v.x; x1 = v.y;
-            }
-            else { x0 = __ldg(ip_cur + h * 64 + g * 8 + 2 * q); x1 = __ldg(ip_cur + h * 64 + g * 8 + 2 * q + 1); }
-            double y0, y1, z0, z1;
-            dmma884(y0, y1, a[6], x0, 0.0, 0.0);
-            dmma884(y0, y1, a[7], x1, y0, y1);
-            dmma884(z0, z1, a[4], y0, 0.0, 0.0);
-            dmma884(z0, z1, a[5], y1, z0, z1);
-            __syncwarp(); // every lane has read its chunk of the slice before the slice is rewritten
-            const int chunk16 = (4 * g + q) ^ dmma_sigma(h);
-            *reinterpret_cast<double2 *>(Ec + h * 64 + chunk16 * 2) = make_double2(z0, z1);
-        }
+        dmma_phase1_inplace<T1, C::G1>(Ec, vec ? nullptr : ip_cur, w, g, q, a[6], a[7], a[4], a[5]);
         __syncthreads();
         // every warp has left item k-1 (phase 2 and flush read the other slot): refill it
         if (t == 0)
@@ -181,24 +302,7 @@ kron_dmma84_kernel(const double *const *__restrict__ A, double *const *__restric
         }
 
         // ---------------- phase 2: factors 1 (index i1 = u) and 0 (index i0 = v), slice pairs
-#pragma unroll
-        for (int jj = 0; jj < P2; ++jj)
-        {
-            const int j   = w * P2 + jj; // slices f = 2j, 2j+1
-            const int h0  = g * 8 + 2 * q;
-            const int sg  = ((g & 1) << 2) | q; // dmma_sigma(h0) == dmma_sigma(h0+1)
-            const double2 v0 = *reinterpret_cast<const double2 *>(Ec + h0 * 64 + ((j ^ sg) << 1));
-            const double2 v1 = *reinterpret_cast<const double2 *>(Ec + (h0 + 1) * 64 + ((j ^ sg) << 1));
-            double y0, y1;
-            dmma884(y0, y1, a[2], v0.x, 0.0, 0.0);
-            dmma884(y0, y1, a[3], v1.x, y0, y1);
-            dmma884(acc[jj][0], acc[jj][1], a[0], y0, acc[jj][0], acc[jj][1]);
-            dmma884(acc[jj][0], acc[jj][1], a[1], y1, acc[jj][0], acc[jj][1]);
-            dmma884(y0, y1, a[2], v0.y, 0.0, 0.0);
-            dmma884(y0, y1, a[3], v1.y, y0, y1);
-            dmma884(acc[jj][2], acc[jj][3], a[0], y0, acc[jj][2], acc[jj][3]);
-            dmma884(acc[jj][2], acc[jj][3], a[1], y1, acc[jj][2], acc[jj][3]);
-        }
+        dmma_phase2_acc<P2, C::G2>(Ec, w, g, q, a[2], a[3], a[0], a[1], acc);
 
         double *o_next = (k + 1 < kend) ? out[k + 1] : nullptr;
         if (o_next != o_cur) // uniform over the CTA
@@ -344,51 +448,12 @@ kron_dmma8_tile4_kernel(const double *const *__restrict__ A, double *const *__re
         mbar_wait(bar + slot, (parity >> slot) & 1u);
         parity ^= 1u << slot;
         // phase 1: the two fastest indices, slice by slice, in place
-#pragma unroll
-        for (int tt = 0; tt < T1; ++tt)
-        {
-            const int h = w * T1 + tt;
-            double x0, x1;
-            if (vec)
-            {
-                const double2 v = *reinterpret_cast<const double2 *>(Ec + h * 64 + g * 8 + 2 * q);
-                x0 = v.x; x1 = v.y;
-            }
-            else { x0 = base[h * 64 + g * 8 + 2 * q]; x1 = base[h * 64 + g * 8 + 2 * q + 1]; }
-            double y0, y1, z0, z1;
-            dmma884(y0, y1, a[6], x0, 0.0, 0.0);
-            dmma884(y0, y1, a[7], x1, y0, y1);
-            dmma884(z0, z1, a[4], y0, 0.0, 0.0);
-            dmma884(z0, z1, a[5], y1, z0, z1);
-            __syncwarp(); // every lane has read its chunk of the slice before the slice is rewritten
-            const int chunk16 = (4 * g + q) ^ dmma_sigma(h);
-            *reinterpret_cast<double2 *>(Ec + h * 64 + chunk16 * 2) = make_double2(z0, z1);
-        }
+        dmma_phase1_inplace<T1, C::G1>(Ec, vec ? nullptr : base, w, g, q, a[6], a[7], a[4], a[5]);
         __syncthreads();
         // everyone has left the previous unit (its write-back read slot (it+2)%3): refill that slot
         if (t == 0) issue(it + 2);
         // phase 2: the next two indices, slice pairs, in place
-#pragma unroll
-        for (int jj = 0; jj < P2; ++jj)
-        {
-            const int j  = w * P2 + jj;
-            const int h0 = g * 8 + 2 * q;
-            const int sg = ((g & 1) << 2) | q;
-            double2 *p0  = reinterpret_cast<double2 *>(Ec + h0 * 64 + ((j ^ sg) << 1));
-            double2 *p1  = reinterpret_cast<double2 *>(Ec + (h0 + 1) * 64 + ((j ^ sg) << 1));
-            const double2 v0 = *p0, v1 = *p1;
-            double y0, y1, r0, r1, r2, r3;
-            dmma884(y0, y1, a[2], v0.x, 0.0, 0.0);
-            dmma884(y0, y1, a[3], v1.x, y0, y1);
-            dmma884(r0, r1, a[0], y0, 0.0, 0.0);
-            dmma884(r0, r1, a[1], y1, r0, r1);
-            dmma884(y0, y1, a[2], v0.y, 0.0, 0.0);
-            dmma884(y0, y1, a[3], v1.y, y0, y1);
-            dmma884(r2, r3, a[0], y0, 0.0, 0.0);
-            dmma884(r2, r3, a[1], y1, r2, r3);
-            *p0 = make_double2(r0, r2);
-            *p1 = make_double2(r1, r3);
-        }
+        dmma_phase2_inplace<P2, C::G2>(Ec, w, g, q, a[2], a[3], a[0], a[1]);
         __syncthreads();
         // linear write-back of the tile (coalesced 128-bit stores)
 #pragma unroll 4
@@ -464,24 +529,7 @@ kron_dmma8_rows2_kernel(const double *const *__restrict__ A, double *const *__re
             cp_async_wait_all();
             __syncthreads(); // tile k is visible; everyone left iteration k-1, so the other buffer is free
             if (k + 1 < kend) fetch(k + 1, tile, E + (int)(((k - k0) & 1) ^ 1) * N);
-#pragma unroll
-            for (int jj = 0; jj < P2; ++jj)
-            {
-                const int j  = w * P2 + jj;
-                const int h0 = g * 8 + 2 * q;
-                const int sg = ((g & 1) << 2) | q;
-                const double2 v0 = *reinterpret_cast<const double2 *>(Ec + h0 * 64 + ((j ^ sg) << 1));
-                const double2 v1 = *reinterpret_cast<const double2 *>(Ec + (h0 + 1) * 64 + ((j ^ sg) << 1));
-                double y0, y1;
-                dmma884(y0, y1, a[2], v0.x, 0.0, 0.0);
-                dmma884(y0, y1, a[3], v1.x, y0, y1);
-                dmma884(acc[jj][0], acc[jj][1], a[0], y0, acc[jj][0], acc[jj][1]);
-                dmma884(acc[jj][0], acc[jj][1], a[1], y1, acc[jj][0], acc[jj][1]);
-                dmma884(y0, y1, a[2], v0.y, 0.0, 0.0);
-                dmma884(y0, y1, a[3], v1.y, y0, y1);
-                dmma884(acc[jj][2], acc[jj][3], a[0], y0, acc[jj][2], acc[jj][3]);
-                dmma884(acc[jj][2], acc[jj][3], a[1], y1, acc[jj][2], acc[jj][3]);
-            }
+            dmma_phase2_acc<P2, C::G2>(Ec, w, g, q, a[2], a[3], a[0], a[1], acc);
             if (o_next != o_cur) // uniform over the CTA
             {
 #pragma unroll
@@ -548,37 +596,48 @@ static cudaError_t launch_dmma8_rows2(int sms, int d, long long N, const double 
     return cudaGetLastError();
 }
 
+} // namespace kron
+#include "kernel_dmma_l2.cuh" // n = 8, d = 6: both passes in one persistent kernel, intermediate resident in L2
+namespace kron
+{
+
 // ------------------------------------------------------------------------------------------------
-// n = 8, d = 2 and 3 (64- and 512-element vectors): one WARP per item, everything in registers.
+// n = 5 .. 8, d = 2 and 3, both precisions: one WARP per item, everything in registers ("dmma", warp per item).
 // ncu on the pair-tile kernel these shapes used (profiles/ncu_pairtile_small_r02.md): n = 8, d = 3 is shared-memory-
 // bound with a third of its wavefronts being bank-conflict replays, the d = 2 items are instruction-bound.  With
 // the chained DMMA of the d = 4 kernel a warp needs no shared memory for the two fastest factors at all: a lane
-// loads its two adjacent elements of every 64-element slice straight from global memory (one coalesced 512-byte
-// request per slice), 4 DMMAs contract the slice's two indices and leave the result on the positions it was loaded
-// from.  d = 3: the remaining factor combines the eight slices with coefficients that are uniform over the warp --
-// its 64 entries travel through 512 bytes of shared memory per warp (cp.async one item ahead, broadcast 128-bit
-// loads), 128 DFMA per lane.  Runs of equal output pointers are summed in the 2 (16) result registers; the flush is
-// two REDG per lane and slice on adjacent elements (sector-complete over the warp).  Data of item s+1 is in flight
-// in registers while item s is computed; pointers travel two items ahead.
+// loads its two adjacent elements (row g, columns 2q, 2q+1) of every n x n slice straight from global memory (one
+// coalesced request per slice), 4 DMMAs contract the slice's two indices and leave the result on the positions it
+// was loaded from.  n < 8 runs on the same 8 x 8 x 4 tiles with the slices and factors ZERO-PADDED in registers (the
+// lanes outside the n x n corner load nothing and add nothing): the tensor pipe has time to spare on these HBM-bound
+// shapes.  Single precision is converted to double at the loads and back at the final adds (more accurate than the
+// fp32 reference, within its 1e-5 tolerance a fortiori) -- there is no fp32 tensor path of sufficient precision.
+// d = 3: the remaining factor combines the n slices with coefficients that are uniform over the warp -- its n^2
+// entries travel through 512 bytes of shared memory per warp (cp.async one item ahead, broadcast 128-bit loads).
+// Runs of equal output pointers are summed in the 2 (2n) result registers; the flush is two REDG per lane and slice on
+// adjacent elements.  Data of item s+1 is in flight in registers while item s is computed; pointers two items ahead.
 inline std::atomic<int> &dmma8s_enabled() { static std::atomic<int> v{1}; return v; } // knob 11
 
-template<int D>
+template<typename T, int NN, int D>
 __global__ void __launch_bounds__(128, (D == 2) ? 6 : 3)
-kron_dmma8s_kernel(const double *const *__restrict__ A, double *const *__restrict__ in, double *const *__restrict__ out,
+kron_dmma8s_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T *const *__restrict__ out,
                    const int lda, const int nb, const long long items_per_warp)
 {
-    constexpr int SL = (D == 2) ? 1 : 8; // 64-element slices per item
-    __shared__ __align__(16) double F0s[4][2][64]; // d = 3: factor 0 of items s, s+1 per warp (column-major 8 x 8)
+    constexpr int SL  = (D == 2) ? 1 : NN;    // n x n slices per item
+    constexpr int NSQ = NN * NN;
+    __shared__ __align__(16) double F0s[4][2][64]; // d = 3: factor 0 of items s, s+1 per warp (column-major, pitch 8, fp64)
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
     const int g = lane >> 2, q = lane & 3;
-    const long long lane_off0 = g + (long long)(2 * q) * lda;
-    const int epos = g * 8 + 2 * q; // my two adjacent elements of a slice
+    // my two adjacent elements of a slice: row g, columns 2q and 2q+1 (outside the n x n corner: zero padding)
+    const bool in0 = (g < NN) && (2 * q < NN), in1 = (g < NN) && (2 * q + 1 < NN);
+    const int epos = g * NN + 2 * q;
+    const long long lane_off0 = g + (long long)(2 * q) * lda; // factor fragment: M[g][2q], M[g][2q+1]
 
     const long long k0 = ((long long)blockIdx.x * 4 + w) * items_per_warp;
     if (k0 >= nb) return;
     const int cnt = (int)((k0 + items_per_warp <= nb) ? items_per_warp : (nb - k0));
 
-    struct Ptrs { const double *ip; double *op; const double *ap[D]; };
+    struct Ptrs { const T *ip; T *op; const T *ap[D]; };
     auto load_ptrs = [&](int s, Ptrs &p) {
         if (s >= cnt) { p.ip = nullptr; p.op = nullptr; return; }
         const long long k = k0 + s;
@@ -586,31 +645,60 @@ kron_dmma8s_kernel(const double *const *__restrict__ A, double *const *__restric
 #pragma unroll
         for (int j = 0; j < D; ++j) p.ap[j] = A[k * D + j];
     };
-    struct Data { double2 x[SL]; double a[4]; };
+    struct Data { double x[SL][2]; double a[4]; };
     auto load_data = [&](const Ptrs &p, Data &dt, int slot) {
         if (!p.ip) return;
-        if (aligned16(p.ip))
+        if constexpr (NN == 8 && sizeof(T) == 8)
         {
+            if (aligned16(p.ip))
+            {
 #pragma unroll
-            for (int h = 0; h < SL; ++h) dt.x[h] = __ldg(reinterpret_cast<const double2 *>(p.ip + h * 64 + epos));
+                for (int h = 0; h < SL; ++h)
+                {
+                    const double2 v = __ldg(reinterpret_cast<const double2 *>(p.ip + h * NSQ + epos));
+                    dt.x[h][0] = v.x; dt.x[h][1] = v.y;
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int h = 0; h < SL; ++h) { dt.x[h][0] = __ldg(p.ip + h * NSQ + epos); dt.x[h][1] = __ldg(p.ip + h * NSQ + epos + 1); }
+            }
         }
         else
         {
 #pragma unroll
-            for (int h = 0; h < SL; ++h) dt.x[h] = make_double2(__ldg(p.ip + h * 64 + epos), __ldg(p.ip + h * 64 + epos + 1));
+            for (int h = 0; h < SL; ++h)
+            {
+                dt.x[h][0] = in0 ? (double)__ldg(p.ip + h * NSQ + epos) : 0.0;
+                dt.x[h][1] = in1 ? (double)__ldg(p.ip + h * NSQ + epos + 1) : 0.0;
+            }
         }
-        // fragments of the two fastest factors: M[g][2q], M[g][2q+1]
-        dt.a[0] = __ldg(p.ap[D - 2] + lane_off0); dt.a[1] = __ldg(p.ap[D - 2] + lane_off0 + lda);
-        dt.a[2] = __ldg(p.ap[D - 1] + lane_off0); dt.a[3] = __ldg(p.ap[D - 1] + lane_off0 + lda);
+        dt.a[0] = in0 ? (double)__ldg(p.ap[D - 2] + lane_off0) : 0.0; dt.a[1] = in1 ? (double)__ldg(p.ap[D - 2] + lane_off0 + lda) : 0.0;
+        dt.a[2] = in0 ? (double)__ldg(p.ap[D - 1] + lane_off0) : 0.0; dt.a[3] = in1 ? (double)__ldg(p.ap[D - 1] + lane_off0 + lda) : 0.0;
         if constexpr (D == 3)
         {
-            // factor 0 -> shared memory, column-major compact: element (r, c) at c*8 + r; two elements per lane
-            const unsigned sa = (unsigned)__cvta_generic_to_shared(&F0s[w][slot][0]);
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
+            // factor 0 -> shared memory as doubles, column-major with pitch 8: element (r, c) at c*8 + r
+            if constexpr (sizeof(T) == 8)
             {
-                const int e = lane + 32 * i, r = e & 7, c = e >> 3;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa + e * 8), "l"(p.ap[0] + r + (long long)c * lda) : "memory");
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(&F0s[w][slot][0]);
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                {
+                    const int e = lane + 32 * i, r = e % NN, c = e / NN;
+                    if (e < NSQ)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa + (c * 8 + r) * 8), "l"(p.ap[0] + r + (long long)c * lda) : "memory");
+                }
+            }
+            else
+            {
+                // fp32 factors are converted on the way: plain loads + shared stores (the values are needed a full item later)
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                {
+                    const int e = lane + 32 * i, r = e % NN, c = e / NN;
+                    if (e < NSQ) F0s[w][slot][c * 8 + r] = (double)__ldg(p.ap[0] + r + (long long)c * lda);
+                }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -640,8 +728,8 @@ kron_dmma8s_kernel(const double *const *__restrict__ A, double *const *__restric
         for (int h = 0; h < SL; ++h)
         {
             double y0, y1;
-            dmma884(y0, y1, d_cur.a[2], d_cur.x[h].x, 0.0, 0.0);
-            dmma884(y0, y1, d_cur.a[3], d_cur.x[h].y, y0, y1);
+            dmma884(y0, y1, d_cur.a[2], d_cur.x[h][0], 0.0, 0.0);
+            dmma884(y0, y1, d_cur.a[3], d_cur.x[h][1], y0, y1);
             if constexpr (D == 2)
             {
                 // the second product accumulates straight onto the run sum (C operand)
@@ -658,17 +746,17 @@ kron_dmma8s_kernel(const double *const *__restrict__ A, double *const *__restric
         {
             const double *F = &F0s[w][s & 1][0];
 #pragma unroll
-            for (int h = 0; h < 8; ++h)
+            for (int h = 0; h < NN; ++h)
             {
-                double f[8]; // column h of factor 0: F0(h', h), h' = 0..7
+                double f[8]; // column h of factor 0: F0(h', h), h' = 0..n-1 (pitch 8; the padding is never used)
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
+                for (int c = 0; c < (NN + 1) / 2; ++c)
                 {
                     const double2 v = *reinterpret_cast<const double2 *>(F + h * 8 + 2 * c);
                     f[2 * c] = v.x; f[2 * c + 1] = v.y;
                 }
 #pragma unroll
-                for (int hp = 0; hp < 8; ++hp)
+                for (int hp = 0; hp < NN; ++hp)
                 {
                     acc[hp][0] = fma(f[hp], z[h][0], acc[hp][0]);
                     acc[hp][1] = fma(f[hp], z[h][1], acc[hp][1]);
@@ -681,8 +769,8 @@ kron_dmma8s_kernel(const double *const *__restrict__ A, double *const *__restric
 #pragma unroll
             for (int h = 0; h < SL; ++h)
             {
-                red_add(p_cur.op + h * 64 + epos, acc[h][0]);
-                red_add(p_cur.op + h * 64 + epos + 1, acc[h][1]);
+                if (in0) red_add(p_cur.op + h * NSQ + epos, (T)acc[h][0]);
+                if (in1) red_add(p_cur.op + h * NSQ + epos + 1, (T)acc[h][1]);
                 acc[h][0] = acc[h][1] = 0.0;
             }
         }
@@ -691,8 +779,8 @@ kron_dmma8s_kernel(const double *const *__restrict__ A, double *const *__restric
     }
 }
 
-template<int D>
-static cudaError_t launch_dmma8s(int sms, const double *const *A, int lda, double *const *in, double *const *out, int nb,
+template<typename T, int NN, int D>
+static cudaError_t launch_dmma8s(int sms, const T *const *A, int lda, T *const *in, T *const *out, int nb,
                                  cudaStream_t st, std::atomic<long long> &launches)
 {
     const long long warps = (long long)sms * ((D == 2) ? 6 : 3) * 4;
@@ -700,9 +788,34 @@ static cudaError_t launch_dmma8s(int sms, const double *const *A, int lda, doubl
     if (ipw > 64) ipw = (ipw + 31) / 32 * 32;
     const long long nw   = ((long long)nb + ipw - 1) / ipw;
     const long long grid = (nw + 3) / 4;
-    kron_dmma8s_kernel<D><<<(int)grid, 128, 0, st>>>(A, in, out, lda, nb, ipw);
+    kron_dmma8s_kernel<T, NN, D><<<(int)grid, 128, 0, st>>>(A, in, out, lda, nb, ipw);
     launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
+}
+
+// which (T, n, d) the warp-per-item kernel takes: measured per shape against the kernels it replaces
+// (tools/dmmaw_session.py, gpurun_out/dmmaw_2.jsonl; fraction of the roofline, new vs old):
+//   fp64  d = 2: n = 5 0.53 / 0.64, n = 6 0.64 / 0.69, n = 7 0.75 / 0.54, n = 8 0.87 / 0.43
+//         d = 3: n = 5 0.49 / 0.37, n = 6 0.57 / 0.41, n = 7 0.65 / 0.32, n = 8 0.68 / 0.44
+//   fp32 (computed in double: the FP64 pipe is the bound) loses everywhere but n = 8, d = 3 (0.39 / 0.35)
+template<typename T>
+static bool dmma8s_takes(int n, int d)
+{
+    const int mode = dmma8s_enabled().load(std::memory_order_relaxed);
+    if (mode == 0 || n < 5 || n > 8 || (d != 2 && d != 3)) return false;
+    if (mode == 2) return true; // everything it can do (development)
+    if (sizeof(T) == 8) return n == 8 || d == 3 || n == 7;
+    return n == 8 && d == 3;
+}
+
+template<typename T>
+static cudaError_t run_dmma8s(int sms, int d, int n, const T *const *A, int lda, T *const *in, T *const *out, int nb,
+                              cudaStream_t st, std::atomic<long long> &launches)
+{
+#define KRON_D8S(NN, DD) if (n == NN && d == DD) return launch_dmma8s<T, NN, DD>(sms, A, lda, in, out, nb, st, launches);
+    KRON_D8S(5, 2) KRON_D8S(6, 2) KRON_D8S(7, 2) KRON_D8S(8, 2) KRON_D8S(5, 3) KRON_D8S(6, 3) KRON_D8S(7, 3) KRON_D8S(8, 3)
+#undef KRON_D8S
+    return cudaErrorNotSupported;
 }
 
 // cudaErrorNotSupported when the shape or type is outside the family.
@@ -713,6 +826,11 @@ static cudaError_t run_dmma(int sms, int d, int n, const T *const *A, int lda, T
                             T *const *scratch = nullptr)
 {
     *remaining = 0;
+    if (dmma8s_takes<T>(n, d))
+    {
+        last_path = "dmma";
+        return run_dmma8s<T>(sms, d, n, A, lda, in, out, nb, st, launches);
+    }
     if constexpr (sizeof(T) == 8)
     {
         if (n == 8 && d == 4)
@@ -720,18 +838,19 @@ static cudaError_t run_dmma(int sms, int d, int n, const T *const *A, int lda, T
             last_path = "dmma";
             return launch_dmma84(sms, A, lda, in, out, nb, st, launches);
         }
-        if (n == 8 && (d == 2 || d == 3) && dmma8s_enabled().load(std::memory_order_relaxed))
-        {
-            last_path = "dmma";
-            return d == 2 ? launch_dmma8s<2>(sms, A, lda, in, out, nb, st, launches)
-                          : launch_dmma8s<3>(sms, A, lda, in, out, nb, st, launches);
-        }
+
         if (n == 8 && (d == 5 || d == 6))
         {
             const long long N = (d == 5) ? 32768 : 262144;
             last_path = "dmma-multipass";
             // scratch != nullptr: `in` is read-only, pass A writes into the scratch vectors and the rest works there
             T *const *work = scratch ? scratch : in;
+            if (d == 6 && dmma86_l2_mode().load(std::memory_order_relaxed) > 0)
+            {
+                // one persistent kernel; the intermediate lives in a library-owned ring in L2, `in` is only read
+                last_path = "dmma-l2";
+                return launch_dmma86_l2(sms, A, lda, in, out, nb, st, launches);
+            }
             if (d == 6)
             {
                 // both passes chunk by chunk, so that pass B reads pass A's result from L2 (common.cuh)

@@ -1,0 +1,390 @@
+// kernel_dmma_l2.cuh -- n = 8, d = 6, double precision: both passes of the DMMA route in ONE persistent kernel whose
+// intermediate never leaves L2 ("dmma-l2" route; included by kernel_dmma.cuh, which provides dmma884 / dmma_sigma).
+//
+// Replaces cuda_kronmult (kronmult_gpu/kronmult.cu:95-130) for the reference's `large` / `realistic` cases
+// (tests/kronmult_bench_gpu.cpp:71-72: n = 8, d = 6, 2 MiB per vector).  The reference moves 2 x 2 MiB through global
+// memory per FACTOR; the two-kernel route of kernel_dmma.cuh moves 3 x 2 MiB per item through HBM (pass A in place in
+// `input`, pass B reads it back); profiles/multipass_chunks_r02.md showed that route to be HBM-bound at 4.2 TB/s and
+// that cutting it into short per-chunk kernels loses more to launch gaps and ramp-up than L2 residency gains.
+//
+// Here the batch is cut into chunks of CH items and ALL work is a single queue of units that persistent CTAs pull
+// with one atomicAdd each:
+//     A(c, item, tile): the four fastest factors on one contiguous 4096-element tile (TMA in, two in-place DMMA
+//                       phases exactly as kron_dmma8_tile4_kernel), sent as ONE bulk copy (shared -> global) to a RING
+//                       of R x CH vectors that belongs to the library (48 MiB by default: it stays in the 126 MB L2 and
+//                       is overwritten before it is ever evicted);
+//     B(c, half column tile): factors 0 and 1 on 64 rows x 32 columns of every item of chunk c, read back from the ring
+//                       (L2 hits), summed over runs of equal output pointers in the accumulator fragment, REDG flush.
+// Queue order: block b = { A(b, *), B(b - LAG, *) }.  B(c) waits for a counter that the A(c) units bump (release /
+// acquire through global memory), A(c) waits for B(c - R) before it overwrites that ring slot.  Every wait is on
+// units with SMALLER queue positions, which running CTAs already hold, so the scheme cannot deadlock whatever the
+// number of resident CTAs (no co-residency assumption, no cooperative launch); waits are bounded and trap.
+// HBM traffic per item: 2 MiB read + the output adds -- the algorithmic bytes.  `input` is not written at all.
+#pragma once
+
+namespace kron
+{
+
+struct Dmma86F
+{
+    static constexpr int CH    = 4;               // items per chunk
+    static constexpr int RMAX  = 8;               // ring slots of CH vectors allocated; R <= RMAX of them are used (knob 13)
+                                                  // B(c) is queued in block c + LAG, 1 <= LAG < R (knob 14)
+    static constexpr int TPI   = 64;              // 4096-element tiles per item = 64-column tiles per item
+    static constexpr long long NV = 262144;       // 8^6
+    static constexpr int AU    = CH * TPI;        // A positions per block
+    static constexpr int BT    = 2 * TPI;         // B units per chunk: 64 rows x 32 columns each (half a column tile)
+    static constexpr int BLOCK = AU + BT;         // queue positions per block
+    static constexpr int NST   = 2;               // shared-memory tile slots
+    static constexpr int CTAS  = 3;               // CTAs per SM (64 KiB of tile slots each, <= 168 registers)
+    static constexpr int SMEM  = NST * 4096 * 8 + 64;
+    static constexpr size_t RING_BYTES = (size_t)RMAX * CH * NV * 8;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// 1-D TMA with an L2 eviction-priority hint (the streamed input must not push the ring out of L2)
+__device__ __forceinline__ void tma_load_1d_hint(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes),
+                   "r"((unsigned)__cvta_generic_to_shared(bar)), "l"(policy) : "memory");
+}
+// thread 0 only: wait until *p >= target (bounded: a lost signal is a bug, not a hang)
+__device__ __forceinline__ void wait_counter(const unsigned *p, unsigned target)
+{
+    if (ld_acquire_u32(p) >= target) return;
+    const long long t0 = clock64();
+    while (ld_acquire_u32(p) < target)
+    {
+        __nanosleep(64);
+        if (clock64() - t0 > 6000000000LL) __trap();
+    }
+}
+
+__global__ void __launch_bounds__(Dmma84::THREADS, Dmma86F::CTAS)
+kron_dmma86_l2_kernel(const double *const *__restrict__ A, double *const *__restrict__ in, double *const *__restrict__ out,
+                      const int lda, const int nb, double *__restrict__ ring, unsigned *__restrict__ ctr, const int nchunks,
+                      const int hints, const int R, const int LAG)
+{
+    using C = Dmma84;
+    using F = Dmma86F;
+    constexpr int N = C::N, T1 = C::T1, P2 = C::P2, NST = F::NST, D = 6;
+    static_assert(NST == 2, "slot arithmetic below is written for two tile slots");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *Rg    = reinterpret_cast<double *>(smem_raw);       // [2][4096]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(Rg + NST * N); // [2] "tile landed"
+    __shared__ long long s_next[2];
+
+    unsigned *queue = ctr, *doneA = ctr + 4, *doneB = ctr + 4 + nchunks;
+    const long long total = (long long)(nchunks + LAG) * F::BLOCK;
+
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int lane_off0 = g + (2 * q) * lda;
+
+    if (t == 0)
+    {
+        for (int i = 0; i < NST; ++i) mbar_init(bar + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint64_t pol_first = 0;
+    if (hints) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+
+    // queue position -> unit.  type 1: A (c, item k, tile), 2: B (c, tile), 0: padding of the block structure
+    struct Unit { int type, c, tile; long long k; };
+    auto decode = [&](long long p) {
+        Unit u{0, 0, 0, 0};
+        if (p >= total) return u;
+        const int b = (int)(p / F::BLOCK), r = (int)(p - (long long)b * F::BLOCK);
+        if (r < F::AU)
+        {
+            u.c = b; u.k = (long long)b * F::CH + r / F::TPI; u.tile = r % F::TPI;
+            u.type = (b < nchunks && u.k < nb) ? 1 : 0;
+        }
+        else
+        {
+            u.c = b - LAG; u.tile = r - F::AU;
+            u.type = (u.c >= 0) ? 2 : 0;
+        }
+        return u;
+    };
+    // tile of an A unit -> shared-memory slot (thread 0 only); unaligned vectors are read from global memory in phase 1
+    auto issue = [&](const Unit &x, int slot) {
+        const double *src = in[x.k] + (long long)x.tile * N;
+        if (aligned16(src))
+        {
+            fence_proxy_async();
+            mbar_arrive_expect_tx(bar + slot, N * 8);
+            if (hints) tma_load_1d_hint(Rg + slot * N, src, N * 8, bar + slot, pol_first);
+            else tma_load_1d(Rg + slot * N, src, N * 8, bar + slot);
+        }
+        else mbar_arrive(bar + slot);
+    };
+    auto load_frags = [&](long long k, double (&a)[8]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+            const double *p0 = A[k * D + 2 + j];
+            a[2 * j]     = __ldg(p0 + lane_off0);
+            a[2 * j + 1] = __ldg(p0 + lane_off0 + lda);
+        }
+    };
+    // thread 0: the bulk store of this CTA's previous A unit is complete -> publish it (release) to the B units
+    int pend_c = -1;
+    auto flush_pending = [&]() {
+        if (t == 0 && pend_c >= 0)
+        {
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            __threadfence();
+            atomicAdd(doneA + pend_c, 1u);
+            pend_c = -1;
+        }
+    };
+
+    long long p_cur = 0;
+    if (t == 0)
+    {
+        p_cur     = (long long)atomicAdd(queue, 1u);
+        s_next[1] = p_cur;
+    }
+    __syncthreads();
+    p_cur = s_next[1];
+    Unit u = decode(p_cur);
+    int s  = 0;           // smem slot of the current unit's tile
+    unsigned parity = 0;  // bit i = phase parity of mbarrier i
+    double a_nxt[8];
+    if (u.type == 1)
+    {
+        if (t == 0) issue(u, 0);
+        load_frags(u.k, a_nxt);
+    }
+
+    for (int it = 0; p_cur < total; ++it)
+    {
+        unsigned pn_reg = 0;
+        if (t == 0) pn_reg = atomicAdd(queue, 1u); // consumed at the unit's first barrier
+        Unit un{0, 0, 0, 0};
+        long long p_nxt = total;
+        // publish the next position (thread 0, before a barrier), read it (everybody, after that barrier), start the
+        // next A unit's tile and factor fragments on their way
+        auto publish = [&]() { if (t == 0) s_next[it & 1] = (long long)pn_reg; };
+        auto pickup  = [&](int pf_slot) {
+            p_nxt = s_next[it & 1];
+            un    = decode(p_nxt);
+            if (un.type == 1)
+            {
+                if (t == 0) issue(un, pf_slot);
+                load_frags(un.k, a_nxt);
+            }
+        };
+
+        if (u.type == 1)
+        {
+            // ---------------------------------------------------------------- A unit (cf. kron_dmma8_tile4_kernel)
+            double *Ec         = Rg + s * N;
+            // the ring slot of chunk c was last read by the B units of chunk c - R: the counter is sampled now (relaxed: the
+            // store below is control-dependent on it) and looked at after phase 2
+            unsigned seenB = (unsigned)F::BT;
+            if (t == 0 && u.c >= R) seenB = ld_relaxed_u32(doneB + (u.c - R));
+            const double *base = in[u.k] + (long long)u.tile * N;
+            const bool vec     = aligned16(base);
+            double a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = a_nxt[i];
+            mbar_wait(bar + s, (parity >> s) & 1u);
+            parity ^= 1u << s;
+            dmma_phase1_inplace<T1, C::G1>(Ec, vec ? nullptr : base, w, g, q, a[6], a[7], a[4], a[5]);
+            publish();
+            __syncthreads();
+            // the other slot is the source of the previous A unit's bulk store: once that is complete, signal it and
+            // refill the slot with the next tile
+            flush_pending();
+            pickup(s ^ 1);
+            dmma_phase2_inplace<P2, C::G2>(Ec, w, g, q, a[2], a[3], a[0], a[1]);
+            if (seenB < (unsigned)F::BT) wait_counter(doneB + (u.c - R), (unsigned)F::BT);
+            fence_proxy_async(); // every thread: its phase-2 writes to the slot become visible to the bulk copy below
+            __syncthreads();
+            // The tile leaves as ONE bulk copy, chunk-swizzled as it stands in shared memory (slice h of the tile has its
+            // 16-byte chunks at c ^ sigma(h)); the B units undo the permutation in their gather addresses.
+            if (t == 0)
+            {
+                double *wb = ring + ((size_t)(u.c % R) * F::CH + (size_t)(u.k - (long long)u.c * F::CH)) * F::NV + (size_t)u.tile * N;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(wb), "r"((unsigned)__cvta_generic_to_shared(Ec)), "r"(N * 8) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                pend_c = u.c;
+            }
+            s ^= 1;
+        }
+        else if (u.type == 2)
+        {
+            // ---------------------------------------------------------------- B unit (cf. kron_dmma8_rows2_kernel)
+            flush_pending(); // (this CTA's own last tile may be one of those the wait below is for)
+            const long long k0 = (long long)u.c * F::CH;
+            const int cnt      = (int)((k0 + F::CH <= nb) ? F::CH : (nb - k0));
+            const int tile = u.tile >> 1, half = u.tile & 1; // 64 rows x 32 columns: 16-byte chunks [16 half, 16 half + 16)
+            const double *rb   = ring + (size_t)(u.c % R) * F::CH * F::NV + (size_t)tile * 64;
+            const int sgT      = dmma_sigma(tile); // the A units stored slice h = tile of every row chunk-swizzled by sigma(h)
+            double *E0 = Rg + s * N, *E1 = Rg + (s ^ 1) * N;
+            auto fetch = [&](int i, double *Eb) {
+                const double *src = rb + (size_t)i * F::NV;
+#pragma unroll 4
+                for (int r = 0; r < N / 4 / C::THREADS; ++r)
+                {
+                    const int c2 = t + r * C::THREADS, h = c2 >> 4, ci = (c2 & 15) + 16 * half;
+                    const unsigned sa = (unsigned)__cvta_generic_to_shared(Eb + h * 64 + ((ci ^ dmma_sigma(h)) << 1));
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + (size_t)h * 4096 + 2 * (ci ^ sgT)) : "memory");
+                }
+                cp_async_commit();
+            };
+            // factor fragments and output pointer one item ahead
+            double fa[4], fn[4];
+            double *o_cur = out[k0], *o_nxt = nullptr;
+            auto load_b = [&](long long k, double (&f)[4]) {
+                const double *p0 = A[k * D + 0], *p1 = A[k * D + 1];
+                f[0] = __ldg(p0 + lane_off0); f[1] = __ldg(p0 + lane_off0 + lda);
+                f[2] = __ldg(p1 + lane_off0); f[3] = __ldg(p1 + lane_off0 + lda);
+            };
+            load_b(k0, fn);
+            if (t == 0) wait_counter(doneA + u.c, (unsigned)(cnt * F::TPI));
+            publish();
+            __syncthreads();
+            fetch(0, E0);
+            constexpr int PB = P2 / 2; // slice pairs per warp in a half tile
+            double acc[PB][4];
+#pragma unroll
+            for (int j = 0; j < PB; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
+            for (int i = 0; i < cnt; ++i)
+            {
+                double *Ec = (i & 1) ? E1 : E0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) fa[j] = fn[j];
+                o_nxt = nullptr;
+                if (i + 1 < cnt) { load_b(k0 + i + 1, fn); o_nxt = out[k0 + i + 1]; }
+                cp_async_wait_all();
+                __syncthreads(); // item i is visible; everyone left item i-1, so the other buffer is free
+                if (i + 1 < cnt) fetch(i + 1, (i & 1) ? E0 : E1);
+                dmma_phase2_acc<PB, PB>(Ec, w, g, q, fa[2], fa[3], fa[0], fa[1], acc, 16 * half);
+                if (o_nxt != o_cur) // uniform over the CTA: end of a run of equal output pointers (or of the unit)
+                {
+#pragma unroll
+                    for (int jj = 0; jj < PB; ++jj)
+                    {
+                        const int j  = 16 * half + w * PB + jj;
+                        const int h0 = g * 8 + 2 * q;
+                        const int sg = ((g & 1) << 2) | q;
+                        *reinterpret_cast<double2 *>(Ec + h0 * 64 + ((j ^ sg) << 1))       = make_double2(acc[jj][0], acc[jj][2]);
+                        *reinterpret_cast<double2 *>(Ec + (h0 + 1) * 64 + ((j ^ sg) << 1)) = make_double2(acc[jj][1], acc[jj][3]);
+                        acc[jj][0] = acc[jj][1] = acc[jj][2] = acc[jj][3] = 0.0;
+                    }
+                    __syncthreads();
+                    double *obase = o_cur + (long long)tile * 64;
+#pragma unroll 4
+                    for (int r = 0; r < N / 4 / C::THREADS; ++r)
+                    {
+                        const int c2 = t + r * C::THREADS, h = c2 >> 4, ci = (c2 & 15) + 16 * half;
+                        const double2 v = *reinterpret_cast<const double2 *>(Ec + h * 64 + ((ci ^ dmma_sigma(h)) << 1));
+                        red_add(obase + (long long)h * 4096 + 2 * ci, v.x);
+                        red_add(obase + (long long)h * 4096 + 2 * ci + 1, v.y);
+                    }
+                }
+                o_cur = o_nxt;
+            }
+            __syncthreads(); // all reads of the ring slot (and of both tile buffers) are done
+            if (t == 0) atomicAdd(doneB + u.c, 1u);
+            pickup(s); // both slots were in use until here: the next A tile starts its way only now
+        }
+        else
+        {
+            flush_pending();
+            publish();
+            __syncthreads();
+            pickup(s);
+        }
+        p_cur = p_nxt;
+        u     = un;
+    }
+    flush_pending();
+}
+
+// The ring, the counters and the event that orders successive launches (they share the ring) belong to the device.
+struct Dmma86State
+{
+    double *ring = nullptr;
+    unsigned *ctr = nullptr;
+    size_t ctr_cap = 0; // in unsigned
+    cudaEvent_t ev = nullptr;
+};
+// knob 12: 0 = the two-kernel route of kernel_dmma.cuh, 1 = this kernel, 2 = this kernel with L2 eviction hints
+// (input evict-first, ring evict-last)
+inline std::atomic<int> &dmma86_l2_mode() { static std::atomic<int> v{2}; return v; }
+inline std::atomic<int> &dmma86_l2_ring() { static std::atomic<int> v{6}; return v; } // knob 13
+inline std::atomic<int> &dmma86_l2_lag() { static std::atomic<int> v{3}; return v; }  // knob 14
+
+static cudaError_t launch_dmma86_l2(int sms, const double *const *A, int lda, double *const *in, double *const *out, int nb,
+                                    cudaStream_t st, std::atomic<long long> &launches)
+{
+    using F = Dmma86F;
+    static std::mutex mtx;
+    static Dmma86State states[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorNotSupported;
+    e = kernel_setup(kron_dmma86_l2_kernel, F::SMEM);
+    if (e != cudaSuccess) return e;
+    const int nchunks  = (nb + F::CH - 1) / F::CH;
+    const size_t need  = 4 + 2 * (size_t)nchunks;
+    std::lock_guard<std::mutex> lk(mtx);
+    Dmma86State &S = states[dev];
+    if (!S.ring)
+    {
+        e = cudaMalloc(&S.ring, F::RING_BYTES);
+        if (e != cudaSuccess) { S.ring = nullptr; return e; }
+        e = cudaEventCreateWithFlags(&S.ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    else
+    {
+        // the previous launch on this device (possibly on another stream) owns the ring until it is done
+        e = cudaStreamWaitEvent(st, S.ev, 0);
+        if (e != cudaSuccess) return e;
+    }
+    if (S.ctr_cap < need)
+    {
+        if (S.ctr) { e = cudaFree(S.ctr); S.ctr = nullptr; S.ctr_cap = 0; if (e != cudaSuccess) return e; }
+        const size_t cap = need * 2 + 1024;
+        e = cudaMalloc(&S.ctr, cap * sizeof(unsigned));
+        if (e != cudaSuccess) { S.ctr = nullptr; return e; }
+        S.ctr_cap = cap;
+    }
+    e = cudaMemsetAsync(S.ctr, 0, need * sizeof(unsigned), st);
+    if (e != cudaSuccess) return e;
+    int R = dmma86_l2_ring().load(std::memory_order_relaxed), LAG = dmma86_l2_lag().load(std::memory_order_relaxed);
+    if (R > F::RMAX) R = F::RMAX;
+    if (R < 2) R = 2;
+    if (LAG >= R) LAG = R - 1;
+    if (LAG < 1) LAG = 1;
+    const long long total    = (long long)(nchunks + LAG) * F::BLOCK;
+    const long long max_grid = (long long)sms * F::CTAS;
+    const int grid           = (int)(total < max_grid ? total : max_grid);
+    kron_dmma86_l2_kernel<<<grid, Dmma84::THREADS, F::SMEM, st>>>(A, in, out, lda, nb, S.ring, S.ctr, nchunks,
+                                                                     dmma86_l2_mode().load(std::memory_order_relaxed) >= 2 ? 1 : 0, R, LAG);
+    launches.fetch_add(1, std::memory_order_relaxed);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return cudaEventRecord(S.ev, st);
+}
+
+} // namespace kron

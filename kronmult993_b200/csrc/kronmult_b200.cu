@@ -325,6 +325,9 @@ static cudaError_t run_tiny(int d, int n, const T *const *A, int lda, T *const *
 // dispatch
 // ----------------------------------------------------------------------------------------------
 template<typename T>
+static int needs_workspace(int d, int n);
+
+template<typename T>
 static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *in, T *const *out, int nb,
                             cudaStream_t st, bool const_in = false, T *const *scratch = nullptr)
 {
@@ -385,7 +388,7 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
     if (force == PATH_DMMA)
     {
         int remaining = 0;
-        if (const_in && !scratch && n == 8 && d > 4) return cudaErrorInvalidValue;
+        if (const_in && !scratch && needs_workspace<T>(d, n)) return cudaErrorInvalidValue;
         e = run_dmma<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path, &remaining, scratch);
         if (e == cudaSuccess && remaining > 0)
             e = run_generic<T>(di, d, n, A, lda, in, out, nb, st, d - remaining, scratch, const_in);
@@ -393,12 +396,17 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
     }
 
     // automatic: most specialised family first
+    if (dmma8s_takes<T>(n, d))
+    {
+        t_last_path = "dmma";
+        return run_dmma8s<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches);
+    }
     e = run_tiny<T>(d, n, A, lda, in, out, nb, st);
     if (e != cudaErrorNotSupported) return e;
     if (!(n == 8 && d == 5)) // n = 8, d = 5: the pairtile pass kernels beat DMMA pass A + a generic single-factor pass (1.8x)
     {
         int remaining = 0;
-        if (const_in && !scratch && sizeof(T) == 8 && n == 8 && d > 4) return cudaErrorInvalidValue;
+        if (const_in && !scratch && sizeof(T) == 8 && n == 8 && needs_workspace<T>(d, n)) return cudaErrorInvalidValue;
         e = run_dmma<T>(di.sms, d, n, A, lda, in, out, nb, st, g_launches, t_last_path, &remaining, scratch);
         if (e == cudaSuccess && remaining > 0)
             e = run_generic<T>(di, d, n, A, lda, in, out, nb, st, d - remaining, scratch, const_in);
@@ -442,7 +450,8 @@ static int needs_workspace(int d, int n)
     }
     if (N * (long long)sizeof(T) <= 512) return 0;                 // tiny
     if (n == 4 && d >= 4 && d <= 6) return 0;                      // regtile / wspec / wspec5
-    if (sizeof(T) == 8 && n == 8) return d > 4 ? 1 : 0;            // dmma
+    if (sizeof(T) == 8 && n == 8)                                  // dmma: d = 6 on the persistent kernel only reads `input`
+        return (d == 5 || (d == 6 && dmma86_l2_mode().load(std::memory_order_relaxed) == 0)) ? 1 : 0;
     if (pairtile_fits<T>(d, n)) return 0;
     return N > (long long)g_generic_resident_kib.load(std::memory_order_relaxed) * 1024 / (long long)sizeof(T) ? 1 : 0;
 }
@@ -613,7 +622,10 @@ int kronmult_b200_set_tuning(int knob, int value)
     if (knob == 8 && value >= 1 && value <= 4) { kron::multipass_streams().store(value); return 0; }
     if (knob == 9 && value >= 0 && value <= 2) { kron::g_tiny_staged.store(value); return 0; } // 2: chunked variant only
     if (knob == 10 && value >= 0 && value <= 2) { kron::g_symh_f32_d5.store(value); return 0; }
-    if (knob == 11) { kron::dmma8s_enabled().store(value ? 1 : 0); return 0; }
+    if (knob == 11 && value >= 0 && value <= 2) { kron::dmma8s_enabled().store(value); return 0; }
+    if (knob == 12 && value >= 0 && value <= 2) { kron::dmma86_l2_mode().store(value); return 0; }
+    if (knob == 13 && value >= 2 && value <= kron::Dmma86F::RMAX) { kron::dmma86_l2_ring().store(value); return 0; }
+    if (knob == 14 && value >= 1 && value < kron::Dmma86F::RMAX) { kron::dmma86_l2_lag().store(value); return 0; }
     return (int)cudaErrorInvalidValue;
 }
 int kronmult_b200_force_path(int path)

@@ -55,6 +55,46 @@ __global__ void __launch_bounds__(256) dmma_kernel(double *out, int iters)
     if (s == -12345.678) out[0] = s;
 }
 
+// Dependent-issue behaviour of the FP64 tensor pipe: every warp runs CH independent chains in which the D fragment of one
+// DMMA is the B fragment of the next (the chaining of kernel_dmma.cuh).  One block of `blockDim.x / 32` warps per SM.
+// clocks[0] = cycles of block 0.
+template<int CH>
+__global__ void dmma_chain_kernel(double *out, long long *clocks, int iters)
+{
+    double a = 1e-3 * (threadIdx.x & 31), x[CH], y[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) { x[i] = 1e-3 * (threadIdx.x + i); y[i] = 0.0; }
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it)
+    {
+#pragma unroll
+        for (int i = 0; i < CH; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+                         : "=d"(x[i]), "=d"(y[i]) : "d"(a), "d"(x[i]), "d"(0.0), "d"(0.0));
+    }
+    const long long t1 = clock64();
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) s += x[i] + y[i];
+    if (s == -12345.678) out[0] = s;
+    if (blockIdx.x == 0 && threadIdx.x == 0) clocks[0] = t1 - t0;
+}
+template<int CH>
+static void dmma_chain(int sms, double *sink, long long *clk, int warps)
+{
+    const int iters = 1 << 15;
+    dmma_chain_kernel<CH><<<sms, warps * 32>>>(sink, clk, iters);
+    CK(cudaDeviceSynchronize());
+    dmma_chain_kernel<CH><<<sms, warps * 32>>>(sink, clk, iters);
+    CK(cudaDeviceSynchronize());
+    long long c = 0;
+    CK(cudaMemcpy(&c, clk, 8, cudaMemcpyDeviceToHost));
+    const double per_warp = (double)c / ((double)iters * CH);           // cycles between DMMAs of one warp
+    const double per_smsp = per_warp / ((warps + 3) / 4 > 0 ? (double)((warps + 3) / 4) : 1.0); // ... of one SM sub-partition
+    printf("{\"bench\": \"dmma_chain\", \"warps_per_sm\": %d, \"chains_per_warp\": %d, \"cycles_per_dmma_per_warp\": %.1f, "
+           "\"cycles_per_dmma_per_smsp\": %.1f}\n", warps, CH, per_warp, per_smsp);
+}
+
 // DFMA and DMMA in ONE instruction stream: per trip 8 DMMA (8 x 256 MACs) and NF x 8 independent DFMA per thread.
 // If the FP64 tensor pipe and the FP64 FMA pipe are separate units the rates add up; if they share the datapath
 // the time is the sum of the two.
@@ -232,6 +272,24 @@ int main(int argc, char **argv)
         mixed<4>("dmma_dfma_mixed", prop.multiProcessorCount, sink);
         mixed<8>("dmma_dfma_mixed", prop.multiProcessorCount, sink);
         mixed<16>("dmma_dfma_mixed", prop.multiProcessorCount, sink);
+        return 0;
+    }
+    if (argc > 1 && std::string(argv[1]) == "dmmalat")
+    {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, 0));
+        double *sink;
+        long long *clk;
+        CK(cudaMalloc(&sink, 1024));
+        CK(cudaMalloc(&clk, 64));
+        const int sms = prop.multiProcessorCount;
+        for (int warps : {4, 8, 12, 16})
+        {
+            dmma_chain<1>(sms, sink, clk, warps);
+            dmma_chain<2>(sms, sink, clk, warps);
+            dmma_chain<4>(sms, sink, clk, warps);
+            dmma_chain<8>(sms, sink, clk, warps);
+        }
         return 0;
     }
     if (argc > 1 && std::string(argv[1]) == "issue")

@@ -52,7 +52,13 @@ def test_reference_large_case_shape(kron, oracle_mod):
     """n = 8, d = 6 (N = 262144 > shared memory): the multi-pass route, 5 distinct outputs."""
     hp = batch.reference_case("large", torch.float64, "cpu", seed=8, nb_cap=12).to_host()
     _check(kron, oracle_mod, hp)
-    assert "multipass" in kron.last_path()
+    assert kron.last_path() == "dmma-l2"  # both passes in one persistent kernel, intermediate in L2 (kernel_dmma_l2.cuh)
+    kron.set_tuning(12, 0)
+    try:
+        _check(kron, oracle_mod, hp)
+        assert kron.last_path() == "dmma-multipass"  # the two-kernel route through `input`
+    finally:
+        kron.set_tuning(12, 2)
     _check(kron, oracle_mod, hp, "generic")  # the shape-agnostic multi-pass route must agree too
     assert kron.last_path() == "generic-multipass"
 
@@ -303,6 +309,69 @@ def test_blocking_entry_plans_shuffled_batches_once(kron, oracle_mod):
         kron.set_tuning(1, 1)
 
 
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("n,d", [(n, d) for n in (5, 6, 7, 8) for d in (2, 3)])
+def test_dmma_warp_per_item_every_shape(kron, oracle_mod, n, d, dt):
+    """kernel_dmma.cuh kron_dmma8s_kernel on every (T, n, d) it is built for (knob 11 = 2; by default only the shapes
+    where it measured faster take it): zero-padded 8 x 8 tiles for n < 8, fp32 computed in double, a single item,
+    ragged warps, runs that straddle warps, strided / windowed factors, vectors that are not 16-byte aligned."""
+    kron.set_tuning(11, 2)
+    try:
+        for alias, kw, extra in (("runs", dict(items_per_output=5), dict(lda=n + 3)),
+                                 ("distinct", {}, dict(matrices="reftest")),
+                                 ("shuffled", dict(items_per_output=4), dict(misalign=1)),
+                                 ("ref", dict(nb_distinct=1), dict(matrices="asgard"))):
+            for nb in (1, 3, 130, 1501):
+                hp = batch.make_problem(d, n, nb, dt, "cpu", seed=n * 100 + d * 10 + nb % 7, alias=alias, **kw, **extra).to_host()
+                _check(kron, oracle_mod, hp)
+                assert kron.last_path() == "dmma"
+    finally:
+        kron.set_tuning(11, 1)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("nb", [1, 2, 4, 5, 9, 13, 24])
+def test_dmma_l2_persistent_kernel(kron, oracle_mod, nb, mode):
+    """n = 8, d = 6 (the reference's `large` / `realistic` shape, tests/kronmult_bench_gpu.cpp:71-72) on the persistent
+    kernel of kernel_dmma_l2.cuh: chunks of 4 items, a partial last chunk, fewer chunks than ring slots and more (the
+    ring wraps at 16 items), runs of equal outputs that straddle chunks, one output for everything, distinct outputs,
+    strided factors, vectors that are not 16-byte aligned; with and without L2 eviction hints (knob 12).  The input
+    vectors must come back untouched (this route only reads them)."""
+    kron.set_tuning(12, mode)
+    try:
+        for alias, kw, extra in (("runs", dict(items_per_output=3), dict(lda=11)),
+                                 ("ref", dict(nb_distinct=1), {}),
+                                 ("distinct", {}, dict(misalign=1))):
+            hp = batch.make_problem(6, 8, nb, torch.float64, "cpu", seed=60 + nb, alias=alias, **kw, **extra).to_host()
+            p = batch.from_host(hp, "cuda")
+            kron.run_problem(p)
+            torch.cuda.synchronize()
+            assert kron.last_path() == "dmma-l2"
+            err = oracle_mod.rel_l2(p.out_slab.cpu().numpy(), oracle_mod.run(hp, "oracle", threads=1))
+            assert err <= 1e-12, (alias, nb, err)
+            assert np.array_equal(p.in_slab.cpu().numpy(), hp.in_slab)
+    finally:
+        kron.set_tuning(12, 2)
+
+
+def test_dmma_l2_launches_on_two_streams_share_the_ring(kron, oracle_mod):
+    """Two stream-ordered calls in flight at once: the second waits for the first (event), results stay exact."""
+    hps = [batch.make_problem(6, 8, 9, torch.float64, "cpu", seed=70 + i, alias="runs", items_per_output=4).to_host()
+           for i in range(2)]
+    ps = [batch.from_host(hp, "cuda") for hp in hps]
+    arrs = [p.pointer_arrays() for p in ps]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for rep in range(3):
+        for p, (A, i, o, w), st in zip(ps, arrs, streams):
+            kron.kronmult_batched(6, 8, A, p.lda, i, o, w, p.nb, stream=st)
+    torch.cuda.synchronize()
+    for p, hp in zip(ps, hps):
+        exp = oracle_mod.run(hp, "oracle", threads=1)
+        three = hp.out_slab + 3.0 * (exp - hp.out_slab)
+        assert oracle_mod.rel_l2(p.out_slab.cpu().numpy(), three) <= 1e-12
+
+
 def _pairtile_shapes(dt):
     """(n, d) the pairtile family accepts: the vector (+ stage, + accumulator) fits in shared memory (fp64 tiles of
     n = 9, 10 are shared by two threads)."""
@@ -389,11 +458,12 @@ def test_read_only_shared_inputs(kron, oracle_mod, n, d, nb):
 
 def test_read_only_input_needs_workspace_for_multipass(kron):
     """Without scratch vectors a shape that has to go through global memory is refused, not silently clobbered."""
-    assert kron.needs_workspace(6, 8, torch.float64) and not kron.needs_workspace(5, 4, torch.float64)
-    p = batch.make_problem(6, 8, 3, torch.float64, "cuda", seed=1)
+    assert kron.needs_workspace(6, 7, torch.float64) and not kron.needs_workspace(5, 4, torch.float64)
+    assert not kron.needs_workspace(6, 8, torch.float64)  # the persistent n = 8, d = 6 kernel only reads `input`
+    p = batch.make_problem(6, 7, 3, torch.float64, "cuda", seed=1)
     A, i, o, _ = p.pointer_arrays()
     with pytest.raises(kron.KronmultError):
-        kron.kronmult_batched_const(6, 8, A, p.lda, i, o, None, 3, dtype=torch.float64)
+        kron.kronmult_batched_const(6, 7, A, p.lda, i, o, None, 3, dtype=torch.float64)
 
 
 @pytest.mark.parametrize("dt", [torch.float64, torch.float32])
