@@ -88,8 +88,9 @@ __device__ __forceinline__ int dmma_sigma(int h) { return (((h >> 3) & 1) << 2) 
 
 // Phase 2 of the n = 8 kernels on a chunk-swizzled 4096-element tile: warp w owns the P2 slice pairs j = w*P2 .. and
 // contracts the two slow indices of the tile (rows h0 = 8g + 2q, h0 + 1), GJ slice pairs (2 GJ chains) at a time.
-// acc[jj][s + 2t] = Out[i0 = g][i1 = 2q + s][f = 2j + t]: the products accumulate onto the run sums.
-template<int P2, int GJ>
+// acc[jj][s + 2t] = Out[i0 = g][i1 = 2q + s][f = 2j + t]: the products accumulate onto the run sums.  RS = row pitch of the
+// buffer in elements (64: a whole 64-column tile; 32: the compact half tiles of kernel_dmma_l2.cuh).
+template<int P2, int GJ, int RS = 64>
 __device__ __forceinline__ void dmma_phase2_acc(const double *__restrict__ Ec, int w, int g, int q, double u0, double u1,
                                                 double v0, double v1, double (&acc)[P2][4], int jbase = 0)
 {
@@ -103,8 +104,8 @@ __device__ __forceinline__ void dmma_phase2_acc(const double *__restrict__ Ec, i
         for (int i = 0; i < GJ; ++i)
         {
             const int j = jbase + w * P2 + j0 + i; // slices f = 2j, 2j+1
-            const double2 a0 = *reinterpret_cast<const double2 *>(Ec + h0 * 64 + ((j ^ sg) << 1));
-            const double2 a1 = *reinterpret_cast<const double2 *>(Ec + (h0 + 1) * 64 + ((j ^ sg) << 1));
+            const double2 a0 = *reinterpret_cast<const double2 *>(Ec + h0 * RS + ((j ^ sg) << 1));
+            const double2 a1 = *reinterpret_cast<const double2 *>(Ec + (h0 + 1) * RS + ((j ^ sg) << 1));
             x0[2 * i] = a0.x; x1[2 * i] = a1.x; x0[2 * i + 1] = a0.y; x1[2 * i + 1] = a1.y;
             c0[2 * i] = acc[j0 + i][0]; c1[2 * i] = acc[j0 + i][1]; c0[2 * i + 1] = acc[j0 + i][2]; c1[2 * i + 1] = acc[j0 + i][3];
         }
@@ -794,7 +795,7 @@ static cudaError_t launch_dmma8s(int sms, const T *const *A, int lda, T *const *
 }
 
 // which (T, n, d) the warp-per-item kernel takes: measured per shape against the kernels it replaces
-// (tools/dmmaw_session.py, gpurun_out/dmmaw_2.jsonl; fraction of the roofline, new vs old):
+// (tools/dmmaw_session.py, profiles/dmma_warp_per_item_r02.jsonl; fraction of the roofline, new vs old):
 //   fp64  d = 2: n = 5 0.53 / 0.64, n = 6 0.64 / 0.69, n = 7 0.75 / 0.54, n = 8 0.87 / 0.43
 //         d = 3: n = 5 0.49 / 0.37, n = 6 0.57 / 0.41, n = 7 0.65 / 0.32, n = 8 0.68 / 0.44
 //   fp32 (computed in double: the FP64 pipe is the bound) loses everywhere but n = 8, d = 3 (0.39 / 0.35)

@@ -36,7 +36,6 @@ struct Dmma86F
     static constexpr int BT    = 2 * TPI;         // B units per chunk: 64 rows x 32 columns each (half a column tile)
     static constexpr int BLOCK = AU + BT;         // queue positions per block
     static constexpr int NST   = 2;               // shared-memory tile slots
-    static constexpr int CTAS  = 3;               // CTAs per SM (64 KiB of tile slots each, <= 168 registers)
     static constexpr int SMEM  = NST * 4096 * 8 + 64;
     static constexpr size_t RING_BYTES = (size_t)RMAX * CH * NV * 8;
 };
@@ -72,14 +71,15 @@ __device__ __forceinline__ void wait_counter(const unsigned *p, unsigned target)
     }
 }
 
-__global__ void __launch_bounds__(Dmma84::THREADS, Dmma86F::CTAS)
+template<int WARPS, int CTAS>
+__global__ void __launch_bounds__(WARPS * 32, CTAS)
 kron_dmma86_l2_kernel(const double *const *__restrict__ A, double *const *__restrict__ in, double *const *__restrict__ out,
                       const int lda, const int nb, double *__restrict__ ring, unsigned *__restrict__ ctr, const int nchunks,
                       const int hints, const int R, const int LAG)
 {
-    using C = Dmma84;
     using F = Dmma86F;
-    constexpr int N = C::N, T1 = C::T1, P2 = C::P2, NST = F::NST, D = 6;
+    constexpr int N = 4096, THREADS = WARPS * 32, T1 = 64 / WARPS, P2 = 32 / WARPS, NST = F::NST, D = 6;
+    constexpr int G1 = T1 < 8 ? T1 : 8, G2 = P2 < 4 ? P2 : 4; // slices / slice pairs a warp works on at once
     static_assert(NST == 2, "slot arithmetic below is written for two tile slots");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *Rg    = reinterpret_cast<double *>(smem_raw);       // [2][4096]
@@ -164,10 +164,12 @@ kron_dmma86_l2_kernel(const double *const *__restrict__ A, double *const *__rest
     int s  = 0;           // smem slot of the current unit's tile
     unsigned parity = 0;  // bit i = phase parity of mbarrier i
     double a_nxt[8];
+    const double *base_nxt = nullptr; // the next A unit's tile in global memory (its alignment decides TMA vs. plain loads)
     if (u.type == 1)
     {
         if (t == 0) issue(u, 0);
         load_frags(u.k, a_nxt);
+        base_nxt = in[u.k] + (long long)u.tile * N;
     }
 
     for (int it = 0; p_cur < total; ++it)
@@ -186,6 +188,7 @@ kron_dmma86_l2_kernel(const double *const *__restrict__ A, double *const *__rest
             {
                 if (t == 0) issue(un, pf_slot);
                 load_frags(un.k, a_nxt);
+                base_nxt = in[un.k] + (long long)un.tile * N;
             }
         };
 
@@ -197,21 +200,21 @@ kron_dmma86_l2_kernel(const double *const *__restrict__ A, double *const *__rest
             // store below is control-dependent on it) and looked at after phase 2
             unsigned seenB = (unsigned)F::BT;
             if (t == 0 && u.c >= R) seenB = ld_relaxed_u32(doneB + (u.c - R));
-            const double *base = in[u.k] + (long long)u.tile * N;
+            const double *base = base_nxt; // fetched while the previous unit was computing
             const bool vec     = aligned16(base);
             double a[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) a[i] = a_nxt[i];
             mbar_wait(bar + s, (parity >> s) & 1u);
             parity ^= 1u << s;
-            dmma_phase1_inplace<T1, C::G1>(Ec, vec ? nullptr : base, w, g, q, a[6], a[7], a[4], a[5]);
+            dmma_phase1_inplace<T1, G1>(Ec, vec ? nullptr : base, w, g, q, a[6], a[7], a[4], a[5]);
             publish();
             __syncthreads();
             // the other slot is the source of the previous A unit's bulk store: once that is complete, signal it and
             // refill the slot with the next tile
             flush_pending();
             pickup(s ^ 1);
-            dmma_phase2_inplace<P2, C::G2>(Ec, w, g, q, a[2], a[3], a[0], a[1]);
+            dmma_phase2_inplace<P2, G2>(Ec, w, g, q, a[2], a[3], a[0], a[1]);
             if (seenB < (unsigned)F::BT) wait_counter(doneB + (u.c - R), (unsigned)F::BT);
             fence_proxy_async(); // every thread: its phase-2 writes to the slot become visible to the bulk copy below
             __syncthreads();
@@ -236,71 +239,86 @@ kron_dmma86_l2_kernel(const double *const *__restrict__ A, double *const *__rest
             const int tile = u.tile >> 1, half = u.tile & 1; // 64 rows x 32 columns: 16-byte chunks [16 half, 16 half + 16)
             const double *rb   = ring + (size_t)(u.c % R) * F::CH * F::NV + (size_t)tile * 64;
             const int sgT      = dmma_sigma(tile); // the A units stored slice h = tile of every row chunk-swizzled by sigma(h)
-            double *E0 = Rg + s * N, *E1 = Rg + (s ^ 1) * N;
-            auto fetch = [&](int i, double *Eb) {
+            // three compact half-tile buffers (64 rows x 32 columns, 16 KiB each) in the two 32 KiB slots: items i+1 and i+2 are
+            // on their way from L2 while item i is computed
+            constexpr int HN = 2048, PB = P2 / 2; // elements per buffer; slice pairs per warp
+            auto buf = [&](int i) { return Rg + (i % 3) * HN; };
+            auto fetch = [&](int i) {
+                double *Eb        = buf(i);
                 const double *src = rb + (size_t)i * F::NV;
 #pragma unroll 4
-                for (int r = 0; r < N / 4 / C::THREADS; ++r)
+                for (int r = 0; r < HN / 2 / THREADS; ++r)
                 {
-                    const int c2 = t + r * C::THREADS, h = c2 >> 4, ci = (c2 & 15) + 16 * half;
-                    const unsigned sa = (unsigned)__cvta_generic_to_shared(Eb + h * 64 + ((ci ^ dmma_sigma(h)) << 1));
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + (size_t)h * 4096 + 2 * (ci ^ sgT)) : "memory");
+                    const int c2 = t + r * THREADS, h = c2 >> 4, ci = c2 & 15;
+                    const unsigned sa = (unsigned)__cvta_generic_to_shared(Eb + h * 32 + ((ci ^ dmma_sigma(h)) << 1));
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + (size_t)h * 4096 + 2 * ((ci + 16 * half) ^ sgT)) : "memory");
                 }
-                cp_async_commit();
             };
-            // factor fragments and output pointer one item ahead
-            double fa[4], fn[4];
-            double *o_cur = out[k0], *o_nxt = nullptr;
-            auto load_b = [&](long long k, double (&f)[4]) {
-                const double *p0 = A[k * D + 0], *p1 = A[k * D + 1];
-                f[0] = __ldg(p0 + lane_off0); f[1] = __ldg(p0 + lane_off0 + lda);
-                f[2] = __ldg(p1 + lane_off0); f[3] = __ldg(p1 + lane_off0 + lda);
-            };
-            load_b(k0, fn);
+            // factor fragments and output pointers of the whole chunk up front (two dependent global loads each)
+            double fa[F::CH][4];
+            double *op[F::CH + 1];
+#pragma unroll
+            for (int i = 0; i < F::CH; ++i)
+            {
+                op[i] = nullptr;
+                fa[i][0] = fa[i][1] = fa[i][2] = fa[i][3] = 0.0;
+                if (i < cnt)
+                {
+                    const double *p0 = A[(k0 + i) * D + 0], *p1 = A[(k0 + i) * D + 1];
+                    fa[i][0] = __ldg(p0 + lane_off0); fa[i][1] = __ldg(p0 + lane_off0 + lda);
+                    fa[i][2] = __ldg(p1 + lane_off0); fa[i][3] = __ldg(p1 + lane_off0 + lda);
+                    op[i] = out[k0 + i];
+                }
+            }
+            op[F::CH] = nullptr;
             if (t == 0) wait_counter(doneA + u.c, (unsigned)(cnt * F::TPI));
             publish();
             __syncthreads();
-            fetch(0, E0);
-            constexpr int PB = P2 / 2; // slice pairs per warp in a half tile
+            fetch(0);
+            cp_async_commit();
+            if (1 < cnt) fetch(1);
+            cp_async_commit();
             double acc[PB][4];
 #pragma unroll
             for (int j = 0; j < PB; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
-            for (int i = 0; i < cnt; ++i)
+#pragma unroll
+            for (int i = 0; i < F::CH; ++i)
             {
-                double *Ec = (i & 1) ? E1 : E0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) fa[j] = fn[j];
-                o_nxt = nullptr;
-                if (i + 1 < cnt) { load_b(k0 + i + 1, fn); o_nxt = out[k0 + i + 1]; }
-                cp_async_wait_all();
-                __syncthreads(); // item i is visible; everyone left item i-1, so the other buffer is free
-                if (i + 1 < cnt) fetch(i + 1, (i & 1) ? E0 : E1);
-                dmma_phase2_acc<PB, PB>(Ec, w, g, q, fa[2], fa[3], fa[0], fa[1], acc, 16 * half);
-                if (o_nxt != o_cur) // uniform over the CTA: end of a run of equal output pointers (or of the unit)
+                if (i < cnt)
                 {
+                    double *Ec = buf(i);
+                    asm volatile("cp.async.wait_group 1;" ::: "memory"); // item i has landed (item i+1 may be pending)
+                    __syncthreads(); // ... for everybody; everyone left item i-1, whose buffer item i+2 takes
+                    if (i + 2 < cnt) fetch(i + 2);
+                    cp_async_commit(); // (possibly empty: keeps the group count in step)
+                    dmma_phase2_acc<PB, PB, 32>(Ec, w, g, q, fa[i][2], fa[i][3], fa[i][0], fa[i][1], acc, 0);
+                    double *o_next = (i + 1 < cnt) ? op[i + 1] : nullptr;
+                    if (o_next != op[i]) // uniform over the CTA: end of a run of equal output pointers (or of the unit)
+                    {
 #pragma unroll
-                    for (int jj = 0; jj < PB; ++jj)
-                    {
-                        const int j  = 16 * half + w * PB + jj;
-                        const int h0 = g * 8 + 2 * q;
-                        const int sg = ((g & 1) << 2) | q;
-                        *reinterpret_cast<double2 *>(Ec + h0 * 64 + ((j ^ sg) << 1))       = make_double2(acc[jj][0], acc[jj][2]);
-                        *reinterpret_cast<double2 *>(Ec + (h0 + 1) * 64 + ((j ^ sg) << 1)) = make_double2(acc[jj][1], acc[jj][3]);
-                        acc[jj][0] = acc[jj][1] = acc[jj][2] = acc[jj][3] = 0.0;
-                    }
-                    __syncthreads();
-                    double *obase = o_cur + (long long)tile * 64;
+                        for (int jj = 0; jj < PB; ++jj)
+                        {
+                            const int j  = w * PB + jj;
+                            const int h0 = g * 8 + 2 * q;
+                            const int sg = ((g & 1) << 2) | q;
+                            *reinterpret_cast<double2 *>(Ec + h0 * 32 + ((j ^ sg) << 1))       = make_double2(acc[jj][0], acc[jj][2]);
+                            *reinterpret_cast<double2 *>(Ec + (h0 + 1) * 32 + ((j ^ sg) << 1)) = make_double2(acc[jj][1], acc[jj][3]);
+                            acc[jj][0] = acc[jj][1] = acc[jj][2] = acc[jj][3] = 0.0;
+                        }
+                        __syncthreads();
+                        double *obase = op[i] + (long long)tile * 64 + 32 * half;
 #pragma unroll 4
-                    for (int r = 0; r < N / 4 / C::THREADS; ++r)
-                    {
-                        const int c2 = t + r * C::THREADS, h = c2 >> 4, ci = (c2 & 15) + 16 * half;
-                        const double2 v = *reinterpret_cast<const double2 *>(Ec + h * 64 + ((ci ^ dmma_sigma(h)) << 1));
-                        red_add(obase + (long long)h * 4096 + 2 * ci, v.x);
-                        red_add(obase + (long long)h * 4096 + 2 * ci + 1, v.y);
+                        for (int r = 0; r < HN / 2 / THREADS; ++r)
+                        {
+                            const int c2 = t + r * THREADS, h = c2 >> 4, ci = c2 & 15;
+                            const double2 v = *reinterpret_cast<const double2 *>(Ec + h * 32 + ((ci ^ dmma_sigma(h)) << 1));
+                            red_add(obase + (long long)h * 4096 + 2 * ci, v.x);
+                            red_add(obase + (long long)h * 4096 + 2 * ci + 1, v.y);
+                        }
                     }
                 }
-                o_cur = o_nxt;
             }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads(); // all reads of the ring slot (and of both tile buffers) are done
             if (t == 0) atomicAdd(doneB + u.c, 1u);
             pickup(s); // both slots were in use until here: the next A tile starts its way only now
@@ -342,7 +360,9 @@ static cudaError_t launch_dmma86_l2(int sms, const double *const *A, int lda, do
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64) return cudaErrorNotSupported;
-    e = kernel_setup(kron_dmma86_l2_kernel, F::SMEM);
+    // 3 CTAs of 4 warps per SM; measured against 2 and 3 CTAs of 8 warps (1.15 / 1.43 / 1.31 ms for 976 items): the more
+    // independent CTAs, the less the tensor pipe idles at their barriers
+    e = kernel_setup(kron_dmma86_l2_kernel<4, 3>, F::SMEM);
     if (e != cudaSuccess) return e;
     const int nchunks  = (nb + F::CH - 1) / F::CH;
     const size_t need  = 4 + 2 * (size_t)nchunks;
@@ -377,10 +397,10 @@ static cudaError_t launch_dmma86_l2(int sms, const double *const *A, int lda, do
     if (LAG >= R) LAG = R - 1;
     if (LAG < 1) LAG = 1;
     const long long total    = (long long)(nchunks + LAG) * F::BLOCK;
-    const long long max_grid = (long long)sms * F::CTAS;
+    const long long max_grid = (long long)sms * 3;
     const int grid           = (int)(total < max_grid ? total : max_grid);
-    kron_dmma86_l2_kernel<<<grid, Dmma84::THREADS, F::SMEM, st>>>(A, in, out, lda, nb, S.ring, S.ctr, nchunks,
-                                                                     dmma86_l2_mode().load(std::memory_order_relaxed) >= 2 ? 1 : 0, R, LAG);
+    const int hints          = dmma86_l2_mode().load(std::memory_order_relaxed) >= 2 ? 1 : 0;
+    kron_dmma86_l2_kernel<4, 3><<<grid, 128, F::SMEM, st>>>(A, in, out, lda, nb, S.ring, S.ctr, nchunks, hints, R, LAG);
     launches.fetch_add(1, std::memory_order_relaxed);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
