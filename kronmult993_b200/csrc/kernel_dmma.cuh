@@ -846,11 +846,12 @@ static cudaError_t run_dmma(int sms, int d, int n, const T *const *A, int lda, T
             last_path = "dmma-multipass";
             // scratch != nullptr: `in` is read-only, pass A writes into the scratch vectors and the rest works there
             T *const *work = scratch ? scratch : in;
-            if (d == 6 && dmma86_l2_mode().load(std::memory_order_relaxed) > 0)
+            if (dmma86_l2_mode().load(std::memory_order_relaxed) > 0)
             {
                 // one persistent kernel; the intermediate lives in a library-owned ring in L2, `in` is only read
                 last_path = "dmma-l2";
-                return launch_dmma86_l2(sms, A, lda, in, out, nb, st, launches);
+                return d == 6 ? launch_dmma8_l2<6>(sms, A, lda, in, out, nb, st, launches)
+                              : launch_dmma8_l2<5>(sms, A, lda, in, out, nb, st, launches);
             }
             if (d == 6)
             {

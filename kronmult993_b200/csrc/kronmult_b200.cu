@@ -403,7 +403,8 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
     }
     e = run_tiny<T>(d, n, A, lda, in, out, nb, st);
     if (e != cudaErrorNotSupported) return e;
-    if (!(n == 8 && d == 5)) // n = 8, d = 5: the pairtile pass kernels beat DMMA pass A + a generic single-factor pass (1.8x)
+    // n = 8, d = 5 without the persistent kernel: the pairtile pass kernels beat DMMA pass A + a generic single-factor pass (1.8x)
+    if (!(n == 8 && d == 5) || (sizeof(T) == 8 && dmma86_l2_mode().load(std::memory_order_relaxed) > 0))
     {
         int remaining = 0;
         if (const_in && !scratch && sizeof(T) == 8 && n == 8 && needs_workspace<T>(d, n)) return cudaErrorInvalidValue;
@@ -451,7 +452,7 @@ static int needs_workspace(int d, int n)
     if (N * (long long)sizeof(T) <= 512) return 0;                 // tiny
     if (n == 4 && d >= 4 && d <= 6) return 0;                      // regtile / wspec / wspec5
     if (sizeof(T) == 8 && n == 8)                                  // dmma: d = 6 on the persistent kernel only reads `input`
-        return (d == 5 || (d == 6 && dmma86_l2_mode().load(std::memory_order_relaxed) == 0)) ? 1 : 0;
+        return (d >= 5 && dmma86_l2_mode().load(std::memory_order_relaxed) == 0) ? 1 : 0;
     if (pairtile_fits<T>(d, n)) return 0;
     return N > (long long)g_generic_resident_kib.load(std::memory_order_relaxed) * 1024 / (long long)sizeof(T) ? 1 : 0;
 }
@@ -624,8 +625,10 @@ int kronmult_b200_set_tuning(int knob, int value)
     if (knob == 10 && value >= 0 && value <= 2) { kron::g_symh_f32_d5.store(value); return 0; }
     if (knob == 11 && value >= 0 && value <= 2) { kron::dmma8s_enabled().store(value); return 0; }
     if (knob == 12 && value >= 0 && value <= 2) { kron::dmma86_l2_mode().store(value); return 0; }
-    if (knob == 13 && value >= 2 && value <= kron::Dmma86F::RMAX) { kron::dmma86_l2_ring().store(value); return 0; }
-    if (knob == 14 && value >= 1 && value < kron::Dmma86F::RMAX) { kron::dmma86_l2_lag().store(value); return 0; }
+    if (knob == 13 && value >= 2 && value <= kron::DmmaL2<6>::RMAX) { kron::dmma86_l2_ring().store(value); return 0; }
+    if (knob == 14 && value >= 1 && value < kron::DmmaL2<6>::RMAX) { kron::dmma86_l2_lag().store(value); return 0; }
+    if (knob == 15 && value >= 2 && value <= kron::DmmaL2<5>::RMAX) { kron::dmma85_l2_ring().store(value); return 0; }
+    if (knob == 16 && value >= 1 && value < kron::DmmaL2<5>::RMAX) { kron::dmma85_l2_lag().store(value); return 0; }
     return (int)cudaErrorInvalidValue;
 }
 int kronmult_b200_force_path(int path)

@@ -82,8 +82,14 @@ def test_needs_workspace_query(kron):
     assert not kron.needs_workspace(5, 6, f64)       # pairtile, 62 KiB
     assert not kron.needs_workspace(6, 6, f32)       # pairtile, 182 KiB single stage
     assert kron.needs_workspace(6, 6, f64)           # pairtile multi-pass
-    assert kron.needs_workspace(5, 8, f64)
-    assert not kron.needs_workspace(6, 8, f64)       # dmma-l2: persistent kernel, intermediate in a library-owned ring
+    # dmma-l2: persistent kernel, intermediate in a library-owned ring; the multi-kernel routes (knob 12 = 0) work in place
+    assert not kron.needs_workspace(6, 8, f64) and not kron.needs_workspace(5, 8, f64)
+    kron.set_tuning(12, 0)
+    try:
+        assert kron.needs_workspace(6, 8, f64) and kron.needs_workspace(5, 8, f64)
+    finally:
+        kron.set_tuning(12, 2)
+    assert kron.needs_workspace(6, 8, f32)
     assert kron.needs_workspace(5, 10, f32) and kron.needs_workspace(6, 10, f64)
     assert kron.needs_workspace(7, 11, f64)          # outside the envelope: generic multi-pass
     assert not kron.needs_workspace(3, 11, f64)      # generic, resident

@@ -330,11 +330,12 @@ def test_dmma_warp_per_item_every_shape(kron, oracle_mod, n, d, dt):
 
 
 @pytest.mark.parametrize("mode", [1, 2])
-@pytest.mark.parametrize("nb", [1, 2, 4, 5, 9, 13, 24])
-def test_dmma_l2_persistent_kernel(kron, oracle_mod, nb, mode):
-    """n = 8, d = 6 (the reference's `large` / `realistic` shape, tests/kronmult_bench_gpu.cpp:71-72) on the persistent
-    kernel of kernel_dmma_l2.cuh: chunks of 4 items, a partial last chunk, fewer chunks than ring slots and more (the
-    ring wraps at 16 items), runs of equal outputs that straddle chunks, one output for everything, distinct outputs,
+@pytest.mark.parametrize("d,nb", [(6, 1), (6, 2), (6, 4), (6, 5), (6, 9), (6, 13), (6, 24), (6, 41),
+                                  (5, 1), (5, 7), (5, 8), (5, 9), (5, 40), (5, 131), (5, 300)])
+def test_dmma_l2_persistent_kernel(kron, oracle_mod, d, nb, mode):
+    """n = 8, d = 6 (the reference's `large` / `realistic` shape, tests/kronmult_bench_gpu.cpp:71-72) and d = 5 on the
+    persistent kernel of kernel_dmma_l2.cuh: chunks of 4 (8) items, a partial last chunk, fewer chunks than ring slots and
+    more (the ring wraps at 24 / 128 items), runs of equal outputs that straddle chunks, one output for everything, distinct outputs,
     strided factors, vectors that are not 16-byte aligned; with and without L2 eviction hints (knob 12).  The input
     vectors must come back untouched (this route only reads them)."""
     kron.set_tuning(12, mode)
@@ -342,7 +343,7 @@ def test_dmma_l2_persistent_kernel(kron, oracle_mod, nb, mode):
         for alias, kw, extra in (("runs", dict(items_per_output=3), dict(lda=11)),
                                  ("ref", dict(nb_distinct=1), {}),
                                  ("distinct", {}, dict(misalign=1))):
-            hp = batch.make_problem(6, 8, nb, torch.float64, "cpu", seed=60 + nb, alias=alias, **kw, **extra).to_host()
+            hp = batch.make_problem(d, 8, nb, torch.float64, "cpu", seed=60 + nb, alias=alias, **kw, **extra).to_host()
             p = batch.from_host(hp, "cuda")
             kron.run_problem(p)
             torch.cuda.synchronize()
@@ -472,13 +473,17 @@ def test_read_only_input_needs_workspace_for_multipass(kron):
 def test_pairtile_multipass(kron, oracle_mod, n, d, nb, dt):
     """Vectors beyond shared memory through the pairtile pass kernels (2 or 3 passes over global memory), forced:
     runs of equal outputs, the reference's few-outputs pattern with lda = 67, ragged unit ranges, misaligned vectors."""
-    if not kron.needs_workspace(d, n, dt):
-        pytest.skip("fits in shared memory: resident kernel")
-    for alias, kw in (("runs", dict(items_per_output=3, lda=n + 1)), ("ref", dict(nb_distinct=2, matrices="reftest")),
-                      ("distinct", dict(misalign=1))):
-        hp = batch.make_problem(d, n, nb, dt, "cpu", seed=n * 11 + d, alias=alias, **kw).to_host()
-        _check(kron, oracle_mod, hp, "pairtile")
-        assert kron.last_path() == "pairtile-multipass"
+    kron.set_tuning(12, 0)  # (the query below then answers for the multi-kernel routes: n = 8 in double is a pairtile shape too)
+    try:
+        if not kron.needs_workspace(d, n, dt):
+            pytest.skip("fits in shared memory: resident kernel")
+        for alias, kw in (("runs", dict(items_per_output=3, lda=n + 1)), ("ref", dict(nb_distinct=2, matrices="reftest")),
+                          ("distinct", dict(misalign=1))):
+            hp = batch.make_problem(d, n, nb, dt, "cpu", seed=n * 11 + d, alias=alias, **kw).to_host()
+            _check(kron, oracle_mod, hp, "pairtile")
+            assert kron.last_path() == "pairtile-multipass"
+    finally:
+        kron.set_tuning(12, 2)
 
 
 def _fuzz_cases(count, seed):
