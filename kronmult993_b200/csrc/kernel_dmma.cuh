@@ -648,60 +648,64 @@ kron_dmma8s_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T 
     };
     struct Data { double x[SL][2]; double a[4]; };
     auto load_data = [&](const Ptrs &p, Data &dt, int slot) {
-        if (!p.ip) return;
-        if constexpr (NN == 8 && sizeof(T) == 8)
+        if (p.ip)
         {
-            if (aligned16(p.ip))
+            if constexpr (NN == 8 && sizeof(T) == 8)
+            {
+                if (aligned16(p.ip))
+                {
+#pragma unroll
+                    for (int h = 0; h < SL; ++h)
+                    {
+                        const double2 v = __ldg(reinterpret_cast<const double2 *>(p.ip + h * NSQ + epos));
+                        dt.x[h][0] = v.x; dt.x[h][1] = v.y;
+                    }
+                }
+                else
+                {
+#pragma unroll
+                    for (int h = 0; h < SL; ++h) { dt.x[h][0] = __ldg(p.ip + h * NSQ + epos); dt.x[h][1] = __ldg(p.ip + h * NSQ + epos + 1); }
+                }
+            }
+            else
             {
 #pragma unroll
                 for (int h = 0; h < SL; ++h)
                 {
-                    const double2 v = __ldg(reinterpret_cast<const double2 *>(p.ip + h * NSQ + epos));
-                    dt.x[h][0] = v.x; dt.x[h][1] = v.y;
+                    dt.x[h][0] = in0 ? (double)__ldg(p.ip + h * NSQ + epos) : 0.0;
+                    dt.x[h][1] = in1 ? (double)__ldg(p.ip + h * NSQ + epos + 1) : 0.0;
                 }
             }
-            else
+            dt.a[0] = in0 ? (double)__ldg(p.ap[D - 2] + lane_off0) : 0.0; dt.a[1] = in1 ? (double)__ldg(p.ap[D - 2] + lane_off0 + lda) : 0.0;
+            dt.a[2] = in0 ? (double)__ldg(p.ap[D - 1] + lane_off0) : 0.0; dt.a[3] = in1 ? (double)__ldg(p.ap[D - 1] + lane_off0 + lda) : 0.0;
+            if constexpr (D == 3)
             {
-#pragma unroll
-                for (int h = 0; h < SL; ++h) { dt.x[h][0] = __ldg(p.ip + h * NSQ + epos); dt.x[h][1] = __ldg(p.ip + h * NSQ + epos + 1); }
-            }
-        }
-        else
-        {
-#pragma unroll
-            for (int h = 0; h < SL; ++h)
-            {
-                dt.x[h][0] = in0 ? (double)__ldg(p.ip + h * NSQ + epos) : 0.0;
-                dt.x[h][1] = in1 ? (double)__ldg(p.ip + h * NSQ + epos + 1) : 0.0;
-            }
-        }
-        dt.a[0] = in0 ? (double)__ldg(p.ap[D - 2] + lane_off0) : 0.0; dt.a[1] = in1 ? (double)__ldg(p.ap[D - 2] + lane_off0 + lda) : 0.0;
-        dt.a[2] = in0 ? (double)__ldg(p.ap[D - 1] + lane_off0) : 0.0; dt.a[3] = in1 ? (double)__ldg(p.ap[D - 1] + lane_off0 + lda) : 0.0;
-        if constexpr (D == 3)
-        {
-            // factor 0 -> shared memory as doubles, column-major with pitch 8: element (r, c) at c*8 + r
-            if constexpr (sizeof(T) == 8)
-            {
-                const unsigned sa = (unsigned)__cvta_generic_to_shared(&F0s[w][slot][0]);
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
+                // factor 0 -> shared memory as doubles, column-major with pitch 8: element (r, c) at c*8 + r
+                if constexpr (sizeof(T) == 8)
                 {
-                    const int e = lane + 32 * i, r = e % NN, c = e / NN;
-                    if (e < NSQ)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa + (c * 8 + r) * 8), "l"(p.ap[0] + r + (long long)c * lda) : "memory");
-                }
-            }
-            else
-            {
-                // fp32 factors are converted on the way: plain loads + shared stores (the values are needed a full item later)
+                    const unsigned sa = (unsigned)__cvta_generic_to_shared(&F0s[w][slot][0]);
 #pragma unroll
-                for (int i = 0; i < 2; ++i)
+                    for (int i = 0; i < 2; ++i)
+                    {
+                        const int e = lane + 32 * i, r = e % NN, c = e / NN;
+                        if (e < NSQ)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa + (c * 8 + r) * 8), "l"(p.ap[0] + r + (long long)c * lda) : "memory");
+                    }
+                }
+                else
                 {
-                    const int e = lane + 32 * i, r = e % NN, c = e / NN;
-                    if (e < NSQ) F0s[w][slot][c * 8 + r] = (double)__ldg(p.ap[0] + r + (long long)c * lda);
+                    // fp32 factors are converted on the way: plain loads + shared stores (the values are needed a full item later)
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+                    {
+                        const int e = lane + 32 * i, r = e % NN, c = e / NN;
+                        if (e < NSQ) F0s[w][slot][c * 8 + r] = (double)__ldg(p.ap[0] + r + (long long)c * lda);
+                    }
                 }
             }
         }
+        // always a group, even an empty one past the last item: the consumer's `wait_group 1` counts groups, and without
+        // it the last item's factor 0 would still be allowed in flight when it is read (found by racecheck, round 2)
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 

@@ -258,7 +258,7 @@ kron_dmma8_l2_kernel(const double *const *__restrict__ A, double *const *__restr
                 auto fetch = [&](int i) {
                     double *Eb        = buf(i);
                     const double *src = rb + (size_t)i * F::NV;
-    #pragma unroll 4
+#pragma unroll 4
                     for (int r = 0; r < HN / 2 / THREADS; ++r)
                     {
                         const int c2 = t + r * THREADS, h = c2 >> 4, ci = c2 & 15;
@@ -269,7 +269,7 @@ kron_dmma8_l2_kernel(const double *const *__restrict__ A, double *const *__restr
                 // factor fragments and output pointers of the whole chunk up front (two dependent global loads each)
                 double fa[F::CH][4];
                 double *op[F::CH + 1];
-    #pragma unroll
+#pragma unroll
                 for (int i = 0; i < F::CH; ++i)
                 {
                     op[i] = nullptr;
@@ -291,9 +291,9 @@ kron_dmma8_l2_kernel(const double *const *__restrict__ A, double *const *__restr
                 if (1 < cnt) fetch(1);
                 cp_async_commit();
                 double acc[PB][4];
-    #pragma unroll
+#pragma unroll
                 for (int j = 0; j < PB; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
-    #pragma unroll
+#pragma unroll
                 for (int i = 0; i < F::CH; ++i)
                 {
                     if (i < cnt)
@@ -307,7 +307,7 @@ kron_dmma8_l2_kernel(const double *const *__restrict__ A, double *const *__restr
                         double *o_next = (i + 1 < cnt) ? op[i + 1] : nullptr;
                         if (o_next != op[i]) // uniform over the CTA: end of a run of equal output pointers (or of the unit)
                         {
-    #pragma unroll
+#pragma unroll
                             for (int jj = 0; jj < PB; ++jj)
                             {
                                 const int j  = w * PB + jj;
@@ -319,7 +319,7 @@ kron_dmma8_l2_kernel(const double *const *__restrict__ A, double *const *__restr
                             }
                             __syncthreads();
                             double *obase = op[i] + (long long)tile * 64 + 32 * half;
-    #pragma unroll 4
+#pragma unroll 4
                             for (int r = 0; r < HN / 2 / THREADS; ++r)
                             {
                                 const int c2 = t + r * THREADS, h = c2 >> 4, ci = c2 & 15;
@@ -405,7 +405,9 @@ kron_dmma8_l2_kernel(const double *const *__restrict__ A, double *const *__restr
                         double *o_next = (i + 1 < cnt) ? op[i + 1] : nullptr;
                         if (o_next != op[i])
                         {
-                            // transpose through the (now free) buffer: row g, columns c + 2q, c + 2q + 1 -> linear REDG
+                            // transpose through the (now free) buffer: row g, columns c + 2q, c + 2q + 1 -> linear REDG.  A warp
+                            // rewrites only the 64-column stripe it alone read, but lane by lane other elements of it
+                            __syncwarp();
 #pragma unroll
                             for (int j = 0; j < CG; ++j)
                             {
