@@ -60,7 +60,8 @@ int kronmult_batched_const_f64_async(int d, int n, const double *const *A, int l
                                      double **out, double **ws, int nb, void *stream);
 int kronmult_batched_const_f32_async(int d, int n, const float *const *A, int lda, const float *const *in, float **out,
                                      float **ws, int nb, void *stream);
-/* 1 if the read-only-input entry points need `ws` for this shape, 0 if not, -1 for invalid arguments */
+/* 1 if the read-only-input entry points need `ws` for this shape, 0 if not, -1 for invalid arguments (the answer
+ * follows knob 12 of kronmult_b200_set_tuning for double-precision n = 8, d = 5 / 6) */
 int kronmult_b200_needs_workspace(int d, int n, int elem_size);
 
 /* Host-buffer entry points with the signature of the reference's CPU flavour
@@ -178,7 +179,14 @@ int kronmult_b200_force_path(int path);
  *        10: 1 / 2 = single-precision n = 4, d = 5 runs on the half-warp-per-item kernel (kernel_symh.cuh, 8 / 12 CTAs
  *            per SM); 0 (default, measured faster) = on the warp-per-item kernel of kernel_sym5.cuh.
  *        11: warp-per-item DMMA kernel (n = 5..8, d = 2, 3, both precisions): 1 (default) = the shapes where it measured
- *            faster, 2 = every shape it supports, 0 = off (tiny / pair-tile kernels). */
+ *            faster, 2 = every shape it supports, 0 = off (tiny / pair-tile kernels).
+ *        12: double-precision n = 8, d = 5 / 6 (vectors of 256 KiB / 2 MiB): 2 (default) = one persistent kernel whose
+ *            intermediate lives in a library-owned 64 MiB ring that stays in L2 (kernel_dmma_l2.cuh; `in` is only
+ *            read, no scratch vectors needed; successive calls on one device share the ring and are ordered by an
+ *            event, also across streams), 1 = the same without the L2 evict-first hint on the input loads,
+ *            0 = the multi-kernel routes that work in place through `in` (round-1 behaviour).
+ *        13 / 14: ring slots in use (2..8, default 6) and queue lag in blocks (default 3) of knob 12's kernel for d = 6.
+ *        15 / 16: the same for d = 5 (2..32, default 24; default 12). */
 int kronmult_b200_set_tuning(int knob, int value);
 
 #ifdef __cplusplus
