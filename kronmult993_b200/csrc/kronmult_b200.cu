@@ -20,6 +20,7 @@
 #include "kernel_symh.cuh"
 #include "kernel_pairtile.cuh"
 #include "kernel_pairpass.cuh"
+#include "kernel_rows2.cuh"
 
 #include <atomic>
 #include <cstdio>
@@ -396,6 +397,11 @@ static cudaError_t dispatch(int d, int n, const T *const *A, int lda, T *const *
     }
 
     // automatic: most specialised family first
+    if (rows2_takes<T>(n, d))
+    {
+        t_last_path = "rows2";
+        return run_rows2<T>(di.sms, n, A, lda, in, out, nb, st, g_launches);
+    }
     if (dmma8s_takes<T>(n, d))
     {
         t_last_path = "dmma";
@@ -629,6 +635,8 @@ int kronmult_b200_set_tuning(int knob, int value)
     if (knob == 14 && value >= 1 && value < kron::DmmaL2<6>::RMAX) { kron::dmma86_l2_lag().store(value); return 0; }
     if (knob == 15 && value >= 2 && value <= kron::DmmaL2<5>::RMAX) { kron::dmma85_l2_ring().store(value); return 0; }
     if (knob == 16 && value >= 1 && value < kron::DmmaL2<5>::RMAX) { kron::dmma85_l2_lag().store(value); return 0; }
+    if (knob == 17 && value >= 0 && value <= 2) { kron::rows2_enabled().store(value); return 0; }
+    if (knob == 18 && value >= 0 && value <= 3) { kron::rows2_variant().store(value); return 0; }
     return (int)cudaErrorInvalidValue;
 }
 int kronmult_b200_force_path(int path)

@@ -329,6 +329,28 @@ def test_dmma_warp_per_item_every_shape(kron, oracle_mod, n, d, dt):
         kron.set_tuning(11, 1)
 
 
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("n", [5, 6, 7, 8, 9, 10])
+def test_rows2_every_shape(kron, oracle_mod, n, dt):
+    """kernel_rows2.cuh kron_rows2_kernel (d = 2, a lane per fibre, floor(32 / n) item slots per warp) on every (T, n) it
+    is built for (knob 17 = 2; by default only the shapes where it measured faster take it): a single item, fewer items
+    than slots, ragged slots, runs of equal outputs that straddle slots and warps, compact aligned data (16-byte chunk
+    copies) as well as strided / windowed factors and vectors that are not 16-byte aligned (element copies)."""
+    kron.set_tuning(17, 2)
+    try:
+        for alias, kw, extra in (("runs", dict(items_per_output=5), {}),
+                                 ("runs", dict(items_per_output=7), dict(lda=n + 3)),
+                                 ("distinct", {}, dict(matrices="reftest")),
+                                 ("shuffled", dict(items_per_output=4), dict(misalign=1)),
+                                 ("ref", dict(nb_distinct=1), dict(matrices="asgard"))):
+            for nb in (1, 2, 7, 130, 1501, 40007):
+                hp = batch.make_problem(2, n, nb, dt, "cpu", seed=n * 100 + nb % 7, alias=alias, **kw, **extra).to_host()
+                _check(kron, oracle_mod, hp)
+                assert kron.last_path() == "rows2"
+    finally:
+        kron.set_tuning(17, 1)
+
+
 @pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("d,nb", [(6, 1), (6, 2), (6, 4), (6, 5), (6, 9), (6, 13), (6, 24), (6, 41),
                                   (5, 1), (5, 7), (5, 8), (5, 9), (5, 40), (5, 131), (5, 300)])
