@@ -26,7 +26,7 @@ namespace kron
 {
 
 inline std::atomic<int> &rows2_enabled() { static std::atomic<int> v{1}; return v; } // knob 17
-inline std::atomic<int> &rows2_variant() { static std::atomic<int> v{0}; return v; } // knob 18: (stages, warps per CTA)
+inline std::atomic<int> &rows2_variant() { static std::atomic<int> v{-1}; return v; } // knob 18: (stages, warps per CTA), -1 = per shape
 
 // which (T, n) the kernel takes for d = 2 (knob 17: 0 = off, 1 = the shapes where it measured faster, 2 = all it is built for)
 template<typename T>
@@ -35,8 +35,12 @@ static bool rows2_takes(int n, int d)
     const int mode = rows2_enabled().load(std::memory_order_relaxed);
     if (mode == 0 || d != 2 || n < 5 || n > 10) return false;
     if (mode == 2) return true;
-    if (sizeof(T) == 8) return n == 9 || n == 10;
-    return false;
+    // measured against the kernels it replaces (tools/rows2_session*.sh, profiles/rows2_r02.md; fraction of the roofline,
+    // rows2 / before):  fp64 n = 5 0.62 / 0.64 (tiny), 6 0.80 / 0.69 (tiny), 7 0.54 / 0.79 (dmma), 8 0.74 / 0.92 (dmma),
+    //                   9 0.52 / 0.32 (pairtile), 10 0.85 / 0.36 (pairtile)
+    //                   fp32 n = 5 0.42 / 0.55, 6 0.69 / 0.76, 7 0.42 / 0.42, 8 0.85 / 0.66, 9 0.37 / 0.31, 10 0.75 / 0.51 (all tiny)
+    if (sizeof(T) == 8) return n == 6 || n == 9 || n == 10;
+    return n >= 8;
 }
 
 // defined in rows2.cu (own translation unit: compiled in parallel); cudaErrorNotSupported outside n = 5 .. 10
@@ -152,7 +156,13 @@ struct Rows2Cfg
     static constexpr int NSQ    = NN * NN;
     static constexpr int VEC    = 16 / (int)sizeof(T);
     static constexpr int MAT    = (NSQ + VEC - 1) / VEC * VEC;   // elements per staged matrix (a multiple of 16 bytes)
-    static constexpr int SLOT0  = 3 * MAT;                       // In, M1, M0
+    // fp64 with odd n: n^2 * 8 is not a multiple of 16, so in a compact batch every other vector / factor starts 8 bytes
+    // off a 16-byte boundary.  Such a matrix is staged SHIFTED by one element (its image starts at element 1 of its
+    // region, which has the spare element) so that source and destination agree modulo 16 and 16-byte copies still
+    // work; the three shift bits of a slot's round travel in a meta word behind the matrices.
+    static constexpr bool SHIFT = sizeof(T) == 8 && (NN % 2) == 1;
+    static constexpr int META   = SHIFT ? VEC : 0;
+    static constexpr int SLOT0  = 3 * MAT + META;                // In, M1, M0 (, meta)
     // an odd number of 16-byte units per slot: the slot-uniform 128-bit loads of the IPW slots then fall into IPW
     // different bank groups and share one wavefront
     static constexpr int SLOT   = ((SLOT0 / VEC) % 2 == 0) ? SLOT0 + VEC : SLOT0;
@@ -174,31 +184,99 @@ __device__ __forceinline__ void rows2_cp_elem(unsigned dst, const T *src)
     else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 
-// lane j of a slot copies its share of one n x n column-major matrix (leading dimension ld) into the compact staged copy
-template<typename T, int NN>
-__device__ __forceinline__ void rows2_copy_matrix(T *dst, const T *__restrict__ src, const int ld, const int j)
+// lane j of a slot copies its share of one n x n column-major matrix (leading dimension ld) into the compact staged copy.
+// Returns the shift of the image in elements (0, or 1 with SHIFT_OK for a compact source 8 bytes off a 16-byte boundary).
+template<typename T, int NN, bool SHIFT_OK>
+__device__ __forceinline__ int rows2_copy_matrix(T *dst, const T *__restrict__ src, const int ld, const int j)
 {
     constexpr int VEC = 16 / (int)sizeof(T), NSQ = NN * NN, NCH = NSQ / VEC, TAIL = NSQ - NCH * VEC;
+    constexpr int RB = NN * (int)sizeof(T); // bytes per column
     const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
-    if (ld == NN && aligned16(src))
+    if (ld == NN && (SHIFT_OK || aligned16(src)))
     {
+        // compact: 16-byte chunks.  SHIFT_OK (fp64, n odd, NCH = (n^2 - 1) / 2): shift 0 = chunks + last element,
+        // shift 1 = first element + chunks, the image one element further into the region.
+        // (One bulk copy -- 1-D TMA -- per matrix by the slot's lane 0 was measured instead: ptxas serialises the
+        // per-lane UBLKCP with an ELECT loop, nine per round; n = 6 gained 8 %, n = 10 and fp32 n = 8 lost 6-15 %,
+        // profiles/rows2_r02.md.)
+        int sh = 0;
+        if constexpr (SHIFT_OK) sh = (int)((reinterpret_cast<uintptr_t>(src) >> 3) & 1);
 #pragma unroll
         for (int q0 = 0; q0 < NCH; q0 += NN)
         {
             const int q = q0 + j;
             if (q0 + NN <= NCH || q < NCH)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + q * 16), "l"(src + q * VEC) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + (q + sh) * 16), "l"(src + q * VEC + sh) : "memory");
         }
-        if constexpr (TAIL > 0)
+        if constexpr (SHIFT_OK)
+        {
+            const int e = sh ? 0 : NSQ - 1;
+            if (j == 0) rows2_cp_elem<T>(sa + (unsigned)(e + sh) * 8u, src + e);
+        }
+        else if constexpr (TAIL > 0)
         {
             if (j < TAIL) rows2_cp_elem<T>(sa + (NCH * VEC + j) * (unsigned)sizeof(T), src + NCH * VEC + j);
         }
+        return sh;
+    }
+    if constexpr (RB % 16 == 0)
+    {
+        if (aligned16(src) && (((long long)ld * (long long)sizeof(T)) & 15) == 0)
+        {
+            // every column starts on a 16-byte boundary (ASGarD: windows into big coefficient matrices, lda = 64 n)
+            constexpr int CPC = RB / 16; // chunks per column
+#pragma unroll
+            for (int q0 = 0; q0 < NCH; q0 += NN)
+            {
+                const int q = q0 + j, c = q / CPC, r = q - c * CPC;
+                if (q0 + NN <= NCH || q < NCH)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + q * 16), "l"(src + (long long)c * ld + r * VEC) : "memory");
+            }
+            return 0;
+        }
+    }
+    // row j of every column: for each column the lanes of a slot read n consecutive elements
+#pragma unroll
+    for (int c = 0; c < NN; ++c) rows2_cp_elem<T>(sa + (c * NN + j) * (unsigned)sizeof(T), src + j + (long long)c * ld);
+    return 0;
+}
+
+// y += M x for the staged factor whose region starts at `reg` (16-byte aligned) and whose image is shifted by sh
+// elements.  Column k of M is read with slot-uniform vector loads whose split into 64- and 128-bit pieces depends on
+// the parity of its first element, k n + sh.  For a shifted image (n odd) the columns are taken in the order
+// 1, 0, 3, 2, ... instead: column k ^ 1 of a shifted image has the alignment of column k of an unshifted one, so one
+// instruction sequence serves both kinds of slot in a warp, with the operand x[k ^ 1] selected once per phase.  The
+// unpaired last column is read with 64-bit loads.
+template<typename T, int NN, bool SHIFT>
+__device__ __forceinline__ void rows2_mul(const T *reg, const int sh, const T (&x)[NN], T (&y)[NN])
+{
+    if constexpr (!SHIFT)
+    {
+        rows2_static_for<0, NN>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            T m[NN];
+            rows2_lds_run<T, NN, k * NN>(reg, m);
+#pragma unroll
+            for (int c = 0; c < NN; ++c) y[c] = m[c] * x[k] + y[c];
+        });
     }
     else
     {
-        // row j of every column: for each column the lanes of a slot read n consecutive elements
+        T xs[NN];
 #pragma unroll
-        for (int c = 0; c < NN; ++c) rows2_cp_elem<T>(sa + (c * NN + j) * (unsigned)sizeof(T), src + j + (long long)c * ld);
+        for (int k = 0; k < NN - 1; ++k) xs[k] = sh ? x[k ^ 1] : x[k];
+        const T *even = reg + (sh ? 1 + NN : 0); // steps with even k: column k (+1 when shifted)
+        const T *odd  = reg + (sh ? 1 - NN : 0); // steps with odd k: column k (-1 when shifted)
+        rows2_static_for<0, NN - 1>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            T m[NN];
+            rows2_lds_run<T, NN, k * NN>((k % 2 == 0) ? even : odd, m);
+#pragma unroll
+            for (int c = 0; c < NN; ++c) y[c] = m[c] * xs[k] + y[c];
+        });
+        const T *last = reg + sh + (NN - 1) * NN;
+#pragma unroll
+        for (int c = 0; c < NN; ++c) y[c] = last[c] * x[NN - 1] + y[c];
     }
 }
 
@@ -237,9 +315,15 @@ kron_rows2_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T *
         if (p.ip)
         {
             T *X = wbase + stage * C::STAGE;
-            rows2_copy_matrix<T, NN>(X, p.ip, NN, j);
-            rows2_copy_matrix<T, NN>(X + C::MAT, p.a1, lda, j);
-            rows2_copy_matrix<T, NN>(X + 2 * C::MAT, p.a0, lda, j);
+            const int sx = rows2_copy_matrix<T, NN, C::SHIFT>(X, p.ip, NN, j);
+            const int s1 = rows2_copy_matrix<T, NN, C::SHIFT>(X + C::MAT, p.a1, lda, j);
+            const int s0 = rows2_copy_matrix<T, NN, C::SHIFT>(X + 2 * C::MAT, p.a0, lda, j);
+            if constexpr (C::SHIFT)
+            {
+                // ordered before the round's reads by the __syncwarp that follows its wait_group; the previous use of
+                // this stage ended with a __syncwarp as well
+                if (j == 0) *reinterpret_cast<int *>(X + 3 * C::MAT) = sx | (s1 << 1) | (s0 << 2);
+            }
         }
         // always a group (possibly empty): the consumer's wait_group counts groups
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -276,34 +360,31 @@ kron_rows2_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T *
         __syncwarp();
 
         T *X = wbase + st_cur * C::STAGE;
+        int sx = 0, s1 = 0, s0 = 0;
+        if constexpr (C::SHIFT)
+        {
+            const int meta = *reinterpret_cast<const int *>(X + 3 * C::MAT);
+            sx = meta & 1; s1 = (meta >> 1) & 1; s0 = (meta >> 2) & 1;
+        }
+        T *Xp = X + sx; // image of In (and of the intermediate)
+        if (lane_on) // (the spare lanes would read slot 0's fibres while their owners rewrite them)
         {
             // phase 1: column j of In times M1, in place
             T x[NN], y[NN];
-            rows2_lds_row<T, NN>(X + j * NN, x);
+            rows2_lds_row<T, NN>(Xp + j * NN, x);
 #pragma unroll
             for (int c = 0; c < NN; ++c) y[c] = T(0);
-            rows2_static_for<0, NN>([&](auto kc) {
-                constexpr int k = decltype(kc)::value;
-                T m[NN];
-                rows2_lds_run<T, NN, k * NN>(X + C::MAT, m);
-#pragma unroll
-                for (int c = 0; c < NN; ++c) y[c] = m[c] * x[k] + y[c];
-            });
-            if (lane_on) rows2_sts_row<T, NN>(X + j * NN, y); // own fibre: no other lane reads or writes it in this phase
+            rows2_mul<T, NN, C::SHIFT>(X + C::MAT, s1, x, y);
+            rows2_sts_row<T, NN>(Xp + j * NN, y); // own fibre: no other lane reads or writes it in this phase
         }
         __syncwarp();
+        if (lane_on)
         {
             // phase 0: row j of the intermediate times M0, onto the run accumulators
             T z[NN];
 #pragma unroll
-            for (int k = 0; k < NN; ++k) z[k] = X[k * NN + j];
-            rows2_static_for<0, NN>([&](auto kc) {
-                constexpr int k = decltype(kc)::value;
-                T m[NN];
-                rows2_lds_run<T, NN, k * NN>(X + 2 * C::MAT, m);
-#pragma unroll
-                for (int r = 0; r < NN; ++r) acc[r] = m[r] * z[k] + acc[r];
-            });
+            for (int k = 0; k < NN; ++k) z[k] = Xp[k * NN + j];
+            rows2_mul<T, NN, C::SHIFT>(X + 2 * C::MAT, s0, z, acc);
         }
         if (op_b != op_a) // end of a run of equal output pointers (op_b is null behind the slot's last item)
         {
@@ -346,7 +427,10 @@ template<typename T, int NN>
 static cudaError_t launch_rows2(int sms, const T *const *A, int lda, T *const *in, T *const *out, int nb, cudaStream_t st,
                                 std::atomic<long long> &launches)
 {
-    switch (rows2_variant().load(std::memory_order_relaxed))
+    int v = rows2_variant().load(std::memory_order_relaxed);
+    // measured (profiles/rows2_r02.md): a third stage pays where a round moves the most bytes
+    if (v < 0) v = (NN == 10 || (sizeof(T) == 4 && NN == 8)) ? 1 : 0;
+    switch (v)
     {
     case 1: return launch_rows2v<T, NN, 3, 4>(sms, A, lda, in, out, nb, st, launches);
     case 2: return launch_rows2v<T, NN, 3, 2>(sms, A, lda, in, out, nb, st, launches);
