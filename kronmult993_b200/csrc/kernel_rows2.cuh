@@ -26,7 +26,7 @@ namespace kron
 {
 
 inline std::atomic<int> &rows2_enabled() { static std::atomic<int> v{1}; return v; } // knob 17
-inline std::atomic<int> &rows2_variant() { static std::atomic<int> v{-1}; return v; } // knob 18: (stages, warps per CTA), -1 = per shape
+inline std::atomic<int> &rows2_variant() { static std::atomic<int> v{-1}; return v; } // knob 18: 0 / 1 = 2 / 3 stages, -1 = per shape
 
 // which (T, n) the kernel takes for d = 2 (knob 17: 0 = off, 1 = the shapes where it measured faster, 2 = all it is built for)
 template<typename T>
@@ -196,9 +196,10 @@ __device__ __forceinline__ int rows2_copy_matrix(T *dst, const T *__restrict__ s
     {
         // compact: 16-byte chunks.  SHIFT_OK (fp64, n odd, NCH = (n^2 - 1) / 2): shift 0 = chunks + last element,
         // shift 1 = first element + chunks, the image one element further into the region.
-        // (One bulk copy -- 1-D TMA -- per matrix by the slot's lane 0 was measured instead: ptxas serialises the
-        // per-lane UBLKCP with an ELECT loop, nine per round; n = 6 gained 8 %, n = 10 and fp32 n = 8 lost 6-15 %,
-        // profiles/rows2_r02.md.)
+        // (Measured instead, both dropped -- profiles/rows2_r02.md: one bulk copy (1-D TMA) per matrix by the slot's lane 0
+        // -- ptxas serialises the per-lane UBLKCP with an ELECT loop, nine per round: n = 6 +8 %, n = 10 and fp32 n = 8
+        // -6..15 %; and the whole warp copying matrix after matrix with the pointers shuffled from the slot's first lane
+        // -- fewer shared-memory wavefronts, but 9 serial copy blocks per round: -13..35 % everywhere.)
         int sh = 0;
         if constexpr (SHIFT_OK) sh = (int)((reinterpret_cast<uintptr_t>(src) >> 3) & 1);
 #pragma unroll
@@ -433,8 +434,7 @@ static cudaError_t launch_rows2(int sms, const T *const *A, int lda, T *const *i
     switch (v)
     {
     case 1: return launch_rows2v<T, NN, 3, 4>(sms, A, lda, in, out, nb, st, launches);
-    case 2: return launch_rows2v<T, NN, 3, 2>(sms, A, lda, in, out, nb, st, launches);
-    case 3: return launch_rows2v<T, NN, 2, 2>(sms, A, lda, in, out, nb, st, launches);
+    // (two-warp CTAs with 2 / 3 stages were measured too: never ahead, profiles/rows2_ab_v1_r02.jsonl)
     default: return launch_rows2v<T, NN, 2, 4>(sms, A, lda, in, out, nb, st, launches);
     }
 }

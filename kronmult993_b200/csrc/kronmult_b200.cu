@@ -636,7 +636,7 @@ int kronmult_b200_set_tuning(int knob, int value)
     if (knob == 15 && value >= 2 && value <= kron::DmmaL2<5>::RMAX) { kron::dmma85_l2_ring().store(value); return 0; }
     if (knob == 16 && value >= 1 && value < kron::DmmaL2<5>::RMAX) { kron::dmma85_l2_lag().store(value); return 0; }
     if (knob == 17 && value >= 0 && value <= 2) { kron::rows2_enabled().store(value); return 0; }
-    if (knob == 18 && value >= -1 && value <= 3) { kron::rows2_variant().store(value); return 0; }
+    if (knob == 18 && value >= -1 && value <= 1) { kron::rows2_variant().store(value); return 0; }
     return (int)cudaErrorInvalidValue;
 }
 int kronmult_b200_force_path(int path)

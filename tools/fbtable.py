@@ -5,7 +5,7 @@ field = sys.argv[2] if len(sys.argv) > 2 else "roofline_frac"
 ns = sorted({r["n"] for r in rows}); ds = sorted({r["d"] for r in rows})
 tab = {(r["n"], r["d"]): r for r in rows}
 code = {"tiny": "t", "pairtile": "p", "pairtile-multipass": "P", "generic": "g", "generic-multipass": "G", "dmma": "D",
-        "dmma-multipass": "M", "dmma-l2": "L", "wspec5": "w", "sym5": "s", "sym4": "h", "wspec": "W", "regtile": "r"}
+        "dmma-multipass": "M", "dmma-l2": "L", "wspec5": "w", "sym5": "s", "sym4": "h", "wspec": "W", "regtile": "r", "rows2": "R"}
 print("n\\d " + "".join(f"{d:>10d}" for d in ds))
 for n in ns:
     line = f"{n:3d} "

@@ -1,7 +1,7 @@
 // How many shared-memory wavefronts does a warp-wide load cost when GROUPS of lanes read the same address?
 // (round-2 design probe for kernel_rows2.cuh: lane (s, j) of item slot s reads a factor column with a slot-uniform
 // 128-bit load, i.e. a warp instruction with IPW distinct addresses.)  One CTA of 8 warps on one SM issues `iters` x 16
-// independent loads per warp; cycles per warp instruction at saturation = wavefronts per instruction (the pipe
+// independent loads per warp (XOR-accumulated, so that arithmetic does not bound the loop); cycles per warp instruction at saturation = wavefronts per instruction (the pipe
 // delivers one wavefront per clock).  Patterns: lane l reads address (l / G) * stride + (l % G) * lane_step.
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(256) probe(const int G, const int stride, cons
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const unsigned base = (unsigned)__cvta_generic_to_shared(sm) + (lane / G) * stride + (lane % G) * lane_step;
-    double acc = 0;
+    unsigned a0 = 0, a1 = 0; // two independent XOR chains: the loop is bound by the shared-memory pipe, not by arithmetic
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it)
     {
@@ -25,21 +25,21 @@ __global__ void __launch_bounds__(256) probe(const int G, const int stride, cons
             const unsigned a = base + ((it * 16 + u) & 15) * 1024; // 16 rotating rows: same bank pattern, different data
             if constexpr (WIDTH == 16)
             {
-                double x, y;
-                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
-                acc += x + y;
+                unsigned x, y, z, w;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(a));
+                a0 ^= x ^ y; a1 ^= z ^ w;
             }
             else
             {
-                double x;
-                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(a));
-                acc += x;
+                unsigned x, y;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(a));
+                a0 ^= x; a1 ^= y;
             }
         }
     }
     const long long t1 = clock64();
     if (threadIdx.x == 0) *clk = t1 - t0;
-    if (acc == 1.2345) *sink = acc;
+    if ((a0 ^ a1) == 0x12345u) *sink = a0;
 }
 
 int main()
