@@ -316,6 +316,7 @@ def test_dmma_warp_per_item_every_shape(kron, oracle_mod, n, d, dt):
     where it measured faster take it): zero-padded 8 x 8 tiles for n < 8, fp32 computed in double, a single item,
     ragged warps, runs that straddle warps, strided / windowed factors, vectors that are not 16-byte aligned."""
     kron.set_tuning(11, 2)
+    kron.set_tuning(17, 0)  # the d = 2 lane-per-fibre kernel (rows2) comes first in the automatic dispatch for some of these shapes
     try:
         for alias, kw, extra in (("runs", dict(items_per_output=5), dict(lda=n + 3)),
                                  ("distinct", {}, dict(matrices="reftest")),
@@ -327,6 +328,7 @@ def test_dmma_warp_per_item_every_shape(kron, oracle_mod, n, d, dt):
                 assert kron.last_path() == "dmma"
     finally:
         kron.set_tuning(11, 1)
+        kron.set_tuning(17, 1)
 
 
 @pytest.mark.parametrize("dt", [torch.float64, torch.float32])
