@@ -188,7 +188,7 @@ int kronmult_b200_force_path(int path);
  *        13 / 14: ring slots in use (2..8, default 6) and queue lag in blocks (default 3) of knob 12's kernel for d = 6.
  *        15 / 16: the same for d = 5 (2..32, default 24; default 12).
  *        17: lane-per-fibre kernel for d = 2 (kernel_rows2.cuh, n = 5..10, both precisions): 1 (default) = the shapes where
- *            it measured faster (double n = 6, 9, 10; single n = 8, 9, 10), 2 = every shape it is built for, 0 = off.
+ *            it measured faster (double n = 6, 9, 10; single n = 7 .. 10), 2 = every shape it is built for, 0 = off.
  *        18: its pipeline depth: 0 / 1 = two / three stages of items per warp, -1 (default) = per shape. */
 int kronmult_b200_set_tuning(int knob, int value);
 

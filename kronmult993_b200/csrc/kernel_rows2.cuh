@@ -1,4 +1,4 @@
-// kernel_rows2.cuh -- d = 2, n = 5 .. 10: one LANE per fibre, floor(32 / n) items side by side in a warp ("rows2").
+// kernel_rows2.cuh -- d = 2, n = 5 .. 10: one LANE per fibre, floor(32 / n) (n odd: floor(32 / (n + 1))) items side by side in a warp ("rows2").
 //
 // Replaces cuda_kronmult_batchelement + cuda_kronmult (kronmult_gpu/kronmult.cu:139-167, :95-130) for the items of
 // 25 .. 100 elements with two factors.  These shapes are HBM-bound with room to spare (n = 10, fp64: 2000 FMAs against
@@ -6,7 +6,7 @@
 // 503 warp instructions per 800-byte item, a quarter of them DFMA (profiles/ncu_pairtile_small_r02.md: run-time tile
 // addressing), and a thread-per-item kernel needs 2 n^2 registers.  Here an item is Out = M1 . In . M0^T with n x n
 // column-major matrices (factor d-1 = M1 acts on the fast index, kronmult.cu:107-118), and a warp works on
-// IPW = floor(32 / n) items at once, lane (s, j) = fibre j of item slot s:
+// IPW items at once (a slot takes n lanes, n + 1 for odd n), lane (s, j) = fibre j of item slot s:
 //   stage    In, M1, M0 of every slot arrive in shared memory with cp.async (16-byte chunks when the data is compact and
 //            aligned, element copies otherwise: lda > n, windows into big matrices, unaligned vectors), one round ahead;
 //   phase 1  lane j reads column j of In (n contiguous values, vector loads), multiplies by M1 -- whose columns are read
@@ -36,11 +36,11 @@ static bool rows2_takes(int n, int d)
     if (mode == 0 || d != 2 || n < 5 || n > 10) return false;
     if (mode == 2) return true;
     // measured against the kernels it replaces (tools/rows2_session*.sh, profiles/rows2_r02.md; fraction of the roofline,
-    // rows2 / before):  fp64 n = 5 0.62 / 0.64 (tiny), 6 0.80 / 0.69 (tiny), 7 0.54 / 0.79 (dmma), 8 0.74 / 0.92 (dmma),
-    //                   9 0.52 / 0.32 (pairtile), 10 0.85 / 0.36 (pairtile)
-    //                   fp32 n = 5 0.42 / 0.55, 6 0.69 / 0.76, 7 0.42 / 0.42, 8 0.85 / 0.66, 9 0.37 / 0.31, 10 0.75 / 0.51 (all tiny)
+    // rows2 / before):  fp64 n = 5 0.62 / 0.64 (tiny), 6 0.80 / 0.69 (tiny), 7 0.72 / 0.79 (dmma), 8 0.74 / 0.92 (dmma),
+    //                   9 0.76 / 0.32 (pairtile), 10 0.85 / 0.36 (pairtile)
+    //                   fp32 n = 5 0.42 / 0.55, 6 0.69 / 0.76, 7 0.49 / 0.42, 8 0.85 / 0.66, 9 0.45 / 0.31, 10 0.75 / 0.51 (all tiny)
     if (sizeof(T) == 8) return n == 6 || n == 9 || n == 10;
-    return n >= 8;
+    return n >= 7;
 }
 
 // defined in rows2.cu (own translation unit: compiled in parallel); cudaErrorNotSupported outside n = 5 .. 10
@@ -152,7 +152,11 @@ __device__ __forceinline__ void rows2_sts_row(T *p, const T (&v)[COUNT])
 template<typename T, int NN, int STAGES_, int WARPS_>
 struct Rows2Cfg
 {
-    static constexpr int IPW    = 32 / NN;                       // item slots per warp
+    // lanes per slot: n rounded up to even.  A 128-bit shared load whose even / odd lane PAIRS disagree on the address takes
+    // the slow path (tools/probes/lds_probe.cu on B200: groups of 9 or 5 lanes 2.1 cycles per warp load, groups of 10,
+    // 8, 4 or 2 lanes 1.3 -- like a warp-wide broadcast), so a slot never starts on an odd lane.
+    static constexpr int LPS    = NN + (NN & 1);
+    static constexpr int IPW    = 32 / LPS;                      // item slots per warp
     static constexpr int NSQ    = NN * NN;
     static constexpr int VEC    = 16 / (int)sizeof(T);
     static constexpr int MAT    = (NSQ + VEC - 1) / VEC * VEC;   // elements per staged matrix (a multiple of 16 bytes)
@@ -199,7 +203,8 @@ __device__ __forceinline__ int rows2_copy_matrix(T *dst, const T *__restrict__ s
         // (Measured instead, both dropped -- profiles/rows2_r02.md: one bulk copy (1-D TMA) per matrix by the slot's lane 0
         // -- ptxas serialises the per-lane UBLKCP with an ELECT loop, nine per round: n = 6 +8 %, n = 10 and fp32 n = 8
         // -6..15 %; and the whole warp copying matrix after matrix with the pointers shuffled from the slot's first lane
-        // -- fewer shared-memory wavefronts, but 9 serial copy blocks per round: -13..35 % everywhere.)
+        // -- fewer shared-memory wavefronts, but 9 serial copy blocks per round: -13..35 % everywhere.  cp.async.ca
+        // instead of .cg for the chunks: -10..35 %.)
         int sh = 0;
         if constexpr (SHIFT_OK) sh = (int)((reinterpret_cast<uintptr_t>(src) >> 3) & 1);
 #pragma unroll
@@ -290,8 +295,8 @@ kron_rows2_kernel(const T *const *__restrict__ A, T *const *__restrict__ in, T *
     static_assert(STAGES == 2 || STAGES == 3, "the pointer pipeline below is written for 2 or 3 stages");
     extern __shared__ __align__(16) unsigned char rows2_smem[];
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
-    const int s = lane / NN, j = lane - s * NN;
-    const bool lane_on = s < C::IPW; // the 32 - IPW * n last lanes of a warp have no fibre
+    const int s = lane / C::LPS, j = lane - s * C::LPS;
+    const bool lane_on = s < C::IPW && j < NN; // the other lanes of a warp have no fibre
     T *const wbase = reinterpret_cast<T *>(rows2_smem) + (size_t)w * (C::STAGES * C::STAGE) + (lane_on ? s : 0) * C::SLOT;
 
     // slot g of the grid owns the L consecutive items from g * L on
