@@ -35,7 +35,7 @@ static bool rows2_takes(int n, int d)
     const int mode = rows2_enabled().load(std::memory_order_relaxed);
     if (mode == 0 || d != 2 || n < 5 || n > 10) return false;
     if (mode == 2) return true;
-    // measured against the kernels it replaces (tools/rows2_session*.sh, profiles/rows2_r02.md; fraction of the roofline,
+    // measured against the kernels it replaces (tools/rows2_session.sh, profiles/rows2_r02.md; fraction of the roofline,
     // rows2 / before):  fp64 n = 5 0.62 / 0.64 (tiny), 6 0.80 / 0.69 (tiny), 7 0.72 / 0.79 (dmma), 8 0.74 / 0.92 (dmma),
     //                   9 0.76 / 0.32 (pairtile), 10 0.85 / 0.36 (pairtile)
     //                   fp32 n = 5 0.42 / 0.55, 6 0.69 / 0.76, 7 0.49 / 0.42, 8 0.85 / 0.66, 9 0.45 / 0.31, 10 0.75 / 0.51 (all tiny)
