@@ -487,8 +487,12 @@ static cudaError_t launch_dmma8_l2(int sms, const double *const *A, int lda, dou
     {
         e = cudaMalloc(&S.ring, F::RING_BYTES);
         if (e != cudaSuccess) { S.ring = nullptr; return e; }
+    }
+    if (!S.ev)
+    {
+        // first launch on this device (or the event could not be created last time): nothing to wait for
         e = cudaEventCreateWithFlags(&S.ev, cudaEventDisableTiming);
-        if (e != cudaSuccess) return e;
+        if (e != cudaSuccess) { S.ev = nullptr; return e; }
     }
     else
     {
