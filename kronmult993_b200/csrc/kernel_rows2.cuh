@@ -10,7 +10,7 @@
 //   stage    In, M1, M0 of every slot arrive in shared memory with cp.async (16-byte chunks when the data is compact and
 //            aligned, element copies otherwise: lda > n, windows into big matrices, unaligned vectors), one round ahead;
 //   phase 1  lane j reads column j of In (n contiguous values, vector loads), multiplies by M1 -- whose columns are read
-//            as slot-uniform vector loads (one wavefront for the whole warp) -- and writes the result back in place;
+//            as slot-uniform vector loads (two wavefronts for the whole warp) -- and writes the result back in place;
 //   phase 0  lane j reads row j of the intermediate (stride n: consecutive lanes, consecutive words), multiplies by M0
 //            and adds onto its n run accumulators.
 // A slot walks CONSECUTIVE batch items, so runs of equal output pointers are summed in registers; at the end of a run
@@ -168,7 +168,7 @@ struct Rows2Cfg
     static constexpr int META   = SHIFT ? VEC : 0;
     static constexpr int SLOT0  = 3 * MAT + META;                // In, M1, M0 (, meta)
     // an odd number of 16-byte units per slot: the slot-uniform 128-bit loads of the IPW slots then fall into IPW
-    // different bank groups and share one wavefront
+    // different bank groups (ncu: 2.1 wavefronts per load for three slots of ten lanes, profiles/rows2_r02.md)
     static constexpr int SLOT   = ((SLOT0 / VEC) % 2 == 0) ? SLOT0 + VEC : SLOT0;
     static constexpr int STAGE  = IPW * SLOT;
     static constexpr int STAGES = STAGES_;                       // 2 or 3: rounds in flight + the one being computed
